@@ -1,0 +1,170 @@
+"""ctypes binding of the C ABI in ``include/fabolas_b200.h``.
+
+PyTorch tensors are only the buffer carrier: every call passes ``tensor.data_ptr()`` of FP64 CUDA
+tensors to the hand-written sm_100a kernels in ``libfabolas_b200.so``.  There is NO CPU fallback:
+importing the library fails loudly if it has not been built, and creating an :class:`Engine` fails
+loudly without a CUDA device.
+
+(Tests may hand an explicitly built emulator library to ``Engine(lib_path=..., device="cpu")`` to
+replay the kernel logic without a GPU -- see ``tests/cusim``; nothing in this package does.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "_lib", "libfabolas_b200.so")
+
+FAB_FAMILY_M52 = 0
+FAB_FAMILY_M52_BASIS = 1
+
+_c_int = ctypes.c_int
+_c_dbl = ctypes.c_double
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); also the list of symbols include/fabolas_b200.h declares.
+SIGNATURES = {
+    "fab_version": (_c_int, []),
+    "fab_ctx_create": (_c_int, [ctypes.POINTER(_vp), _c_int, _vp]),
+    "fab_ctx_destroy": (_c_int, [_vp]),
+    "fab_last_error": (ctypes.c_char_p, [_vp]),
+    "fab_gp_set_data": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_dbl, _c_dbl]),
+    "fab_gp_loglik_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
+    "fab_gp_factorize_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
+    "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
+}
+
+
+class FabolasError(RuntimeError):
+    pass
+
+
+_LIBS: dict = {}
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise FabolasError(
+            f"{path} is missing: build the CUDA extension first (python -m fabolas_b200.build). "
+            "fabolas_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIBS[path] = lib
+    return lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else _vp(t.data_ptr())
+
+
+class Engine:
+    """One ``fab_ctx``: a device, a stream and the resident GP problem / factorised models."""
+
+    def __init__(self, device: Optional[str] = None, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        if lib_path is None:
+            if not torch.cuda.is_available():
+                raise FabolasError("fabolas_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+            self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+            if self.device.type != "cuda":
+                raise FabolasError("fabolas_b200 engines run on CUDA devices only")
+            index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self.device = torch.device("cuda", index)
+            with torch.cuda.device(index):
+                stream = torch.cuda.current_stream().cuda_stream
+        else:  # emulator library handed in by a test
+            self.device = torch.device(device or "cpu")
+            index, stream = 0, 0
+        self._ctx = _vp()
+        rc = self.lib.fab_ctx_create(ctypes.byref(self._ctx), index, _vp(stream))
+        if rc != 0:
+            raise FabolasError(f"fab_ctx_create failed with {rc}")
+        self.family = None
+        self.N = self.D = self.d = self.Pk = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.fab_ctx_destroy(self._ctx)
+            self._ctx = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.fab_last_error(self._ctx)
+            raise FabolasError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def tensor(self, a, dtype=torch.float64) -> torch.Tensor:
+        """Move/convert `a` to a contiguous tensor of `dtype` on the engine's device."""
+        t = torch.as_tensor(a, dtype=dtype)
+        return t.to(self.device).contiguous()
+
+    def empty(self, *shape, dtype=torch.float64) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def set_data(self, family: int, X, y, mean: float, amp_mult: Optional[float] = None):
+        X = self.tensor(X)
+        y = self.tensor(y).reshape(-1)
+        if X.dim() != 2 or y.numel() != X.shape[0]:
+            raise ValueError("X must be (N, D) and y (N,)")
+        N, D = X.shape
+        amp_mult = float(D if amp_mult is None else amp_mult)
+        self._check(self.lib.fab_gp_set_data(self._ctx, family, _ptr(X), N, D, _ptr(y), float(mean), amp_mult),
+                    "fab_gp_set_data")
+        self.family, self.N, self.D = family, N, D
+        self.d = D - 1 if family == FAB_FAMILY_M52_BASIS else D
+        self.Pk = self.d + 3 if family == FAB_FAMILY_M52_BASIS else self.d + 1
+
+    def _theta(self, theta, yerr2):
+        theta = self.tensor(theta)
+        if theta.dim() == 1:
+            theta = theta[None]
+        if theta.shape[1] != self.Pk:
+            raise ValueError(f"theta must have {self.Pk} columns, got {theta.shape[1]}")
+        yerr2 = self.tensor(yerr2).reshape(-1)
+        if yerr2.numel() == 1 and theta.shape[0] > 1:
+            yerr2 = yerr2.expand(theta.shape[0]).contiguous()
+        if yerr2.numel() != theta.shape[0]:
+            raise ValueError("one yerr2 per theta row")
+        return theta, yerr2
+
+    def loglik(self, theta, yerr2, grad: bool = False):
+        theta, yerr2 = self._theta(theta, yerr2)
+        B = theta.shape[0]
+        ll = self.empty(B)
+        info = self.empty(B, dtype=torch.int32)
+        g = self.empty(B, self.Pk + 1) if grad else None
+        self._check(self.lib.fab_gp_loglik_batch(self._ctx, _ptr(theta), _ptr(yerr2), B, _ptr(ll), _ptr(g),
+                                                 _ptr(info)), "fab_gp_loglik_batch")
+        return (ll, g, info) if grad else (ll, info)
+
+    def factorize(self, theta, yerr2):
+        theta, yerr2 = self._theta(theta, yerr2)
+        B = theta.shape[0]
+        ll = self.empty(B)
+        info = self.empty(B, dtype=torch.int32)
+        self._check(self.lib.fab_gp_factorize_batch(self._ctx, _ptr(theta), _ptr(yerr2), B, _ptr(ll), _ptr(info)),
+                    "fab_gp_factorize_batch")
+        self.B = B
+        return ll, info
+
+    def debug_factor(self, b: int) -> torch.Tensor:
+        L = self.empty(self.N, self.N)
+        self._check(self.lib.fab_gp_debug_get_factor(self._ctx, b, _ptr(L)), "fab_gp_debug_get_factor")
+        return L

@@ -1,0 +1,187 @@
+// api.cu -- C ABI (include/fabolas_b200.h): context, workspaces, launch logic.
+#include "../../include/fabolas_b200.h"
+#include "gp_factor.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+using namespace fab;
+
+struct fab_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // problem
+    bool has_data = false;
+    GpData gd{};
+    double* dX = nullptr; size_t capX = 0;
+    double* dy = nullptr; size_t capy = 0;
+    // workspaces
+    GpWork wk{};
+    size_t capL = 0, capD = 0, capZ = 0;
+    int wsB = 0;            // walkers the factor workspace currently describes
+    bool factored = false;
+    int smem_optin = 232448;
+};
+
+namespace {
+
+int fail(fab_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define FAB_CUDA(c, call)                                                      \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) return fail((c), FAB_ECUDA, #call, e_);         \
+    } while (0)
+
+template <typename T>
+int ensure(fab_ctx* c, T** p, size_t* cap, size_t need) {
+    if (*cap >= need && *p) return FAB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    if (cudaMalloc(reinterpret_cast<void**>(p), need * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, FAB_ENOMEM, "workspace allocation failed");
+    }
+    *cap = need;
+    return FAB_OK;
+}
+
+int pk_of(const GpData& gd) { return gd.family == FAB_FAMILY_M52_BASIS ? gd.d + 3 : gd.d + 1; }
+
+__global__ void untile_kernel(const double* __restrict__ Lw, double* __restrict__ out, int N, int NT) {
+    const int i = blockIdx.x;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        double v = 0.0;
+        if (j <= i) {
+            const int I = i / TS, J = j / TS;
+            v = Lw[(size_t)tri_index(I, J) * TILE_ELEMS + tix(i % TS, j % TS)];
+        }
+        out[(size_t)i * N + j] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int fab_version(void) { return 100; }
+
+int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
+    if (!out) return FAB_EINVAL;
+    fab_ctx* c = new (std::nothrow) fab_ctx();
+    if (!c) return FAB_ENOMEM;
+    c->device = device;
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return FAB_ECUDA; }
+#ifndef FAB_CUSIM
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess && v > 0)
+        c->smem_optin = v;
+    cudaFuncSetAttribute(gp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+#endif
+    *out = c;
+    return FAB_OK;
+}
+
+int fab_ctx_destroy(fab_ctx* c) {
+    if (!c) return FAB_EINVAL;
+    cudaSetDevice(c->device);
+    cudaFree(c->dX); cudaFree(c->dy);
+    cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha);
+    delete c;
+    return FAB_OK;
+}
+
+const char* fab_last_error(const fab_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int fab_gp_set_data(fab_ctx* c, int family, const double* X, int N, int D, const double* y, double mean,
+                    double amp_mult) {
+    if (!c || !X || !y) return fail(c, FAB_EINVAL, "null pointer");
+    if (family != FAB_FAMILY_M52 && family != FAB_FAMILY_M52_BASIS) return fail(c, FAB_EINVAL, "unknown family");
+    const int d = family == FAB_FAMILY_M52_BASIS ? D - 1 : D;
+    if (N < 1 || d < 1 || d > MAX_D) return fail(c, FAB_EINVAL, "need N >= 1 and 1 <= d <= 8 Matern axes");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, &c->dX, &c->capX, (size_t)N * D)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->dy, &c->capy, (size_t)N)) != FAB_OK) return rc;
+    FAB_CUDA(c, cudaMemcpyAsync(c->dX, X, sizeof(double) * N * D, cudaMemcpyDeviceToDevice, c->stream));
+    FAB_CUDA(c, cudaMemcpyAsync(c->dy, y, sizeof(double) * N, cudaMemcpyDeviceToDevice, c->stream));
+    GpData& gd = c->gd;
+    gd.X = c->dX; gd.y = c->dy; gd.mean = mean; gd.amp_mult = amp_mult;
+    gd.N = N; gd.D = D; gd.d = d; gd.family = family;
+    gd.NT = (N + TS - 1) / TS; gd.Np = gd.NT * TS;
+    gd.Pk = pk_of(gd);
+    c->has_data = true;
+    c->factored = false;
+    return FAB_OK;
+}
+
+static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info,
+                         bool store) {
+    const GpData& gd = c->gd;
+    const int ntiles = gd.NT * (gd.NT + 1) / 2;
+    // slots: everything if it fits, else as many as shared memory allows (>= 4 needed)
+    int nslot = ntiles < MAX_SLOTS ? ntiles : MAX_SLOTS;
+    while (nslot > 0 && factor_smem_bytes(nslot, gd.Np, gd.d) > (size_t)c->smem_optin) --nslot;
+    const bool fits = nslot >= ntiles;
+    if (nslot < 4 && !fits) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA factor kernel");
+    const bool need_ws = store || !fits;
+    if (need_ws) {
+        int rc;
+        if ((rc = ensure(c, &c->wk.Lw, &c->capL, (size_t)B * ntiles * TILE_ELEMS)) != FAB_OK) return rc;
+        if ((rc = ensure(c, &c->wk.Dinv, &c->capD, (size_t)B * gd.NT * 512)) != FAB_OK) return rc;
+        if ((rc = ensure(c, &c->wk.zvec, &c->capZ, (size_t)B * gd.Np)) != FAB_OK) return rc;
+    }
+    FactorArgs a;
+    a.gd = gd; a.wk = c->wk;
+    if (!need_ws) { a.wk.Lw = nullptr; a.wk.Dinv = nullptr; a.wk.zvec = nullptr; }
+    a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info;
+    a.nslot = nslot; a.store = need_ws ? 1 : 0;
+    const size_t smem = factor_smem_bytes(nslot, gd.Np, gd.d);
+    FAB_LAUNCH(gp_factor_kernel, B, NTHREADS, smem, c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    if (need_ws) { c->wsB = B; c->factored = true; }
+    return FAB_OK;
+}
+
+int fab_gp_loglik_batch(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, double* grad,
+                        int* info) {
+    if (!c) return FAB_EINVAL;
+    if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
+    if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    int rc = launch_factor(c, theta, yerr2, B, ll, info, grad != nullptr);
+    if (rc != FAB_OK) return rc;
+    if (grad) return fail(c, FAB_EUNSUPPORTED, "gradient kernel not built yet");
+    return FAB_OK;
+}
+
+int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info) {
+    if (!c) return FAB_EINVAL;
+    if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
+    if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    return launch_factor(c, theta, yerr2, B, ll, info, true);
+}
+
+int fab_gp_debug_get_factor(fab_ctx* c, int b, double* L_out) {
+    if (!c || !L_out) return FAB_EINVAL;
+    if (!c->factored || b < 0 || b >= c->wsB) return fail(c, FAB_ESTATE, "no factor workspace for this walker");
+    const GpData& gd = c->gd;
+    const int ntiles = gd.NT * (gd.NT + 1) / 2;
+    FAB_LAUNCH(untile_kernel, gd.N, 128, 0, c->stream, c->wk.Lw + (size_t)b * ntiles * TILE_ELEMS, L_out, gd.N,
+               gd.NT);
+    FAB_CUDA(c, cudaGetLastError());
+    return FAB_OK;
+}
+
+}  // extern "C"

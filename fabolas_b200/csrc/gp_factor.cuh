@@ -1,0 +1,190 @@
+// gp_factor.cuh -- kernel A: fused covariance build + tiled Cholesky + forward solve + log-likelihood.
+//
+// One CTA (256 threads, one SM) per walker / hyper-parameter sample.  Replaces, for a whole batch of
+// walkers at once, the george calls  GP.compute (fabolas.py:62, entropy_search.py:73)  and
+// GP.log_likelihood (fabolas.py:66, entropy_search.py:77):
+//     K = k(X, X) + (yerr^2 + 1.25e-12) I ;  K = L L^T ;  z = L^-1 (y - mean)
+//     ll = -0.5 (N log 2pi + 2 sum log L_ii) - 0.5 z.z          (-inf when K is not positive definite)
+// The covariance matrix is never materialised in HBM: tiles are generated from the N x D
+// observation matrix (staged once in shared memory, pre-scaled by 1/sqrt(M_k)) straight into the
+// shared-memory tile cache and consumed by the left-looking block-column factorisation.  Factor
+// tiles are written through to the HBM workspace only when a later stage (gradient, prediction)
+// needs them.
+#pragma once
+#include "gp_common.cuh"
+
+namespace fab {
+
+struct FactorArgs {
+    GpData gd;
+    GpWork wk;
+    const double* theta;   // B x Pk
+    const double* yerr2;   // B
+    double* ll;            // B
+    int* info;             // B   0 ok, k>0: leading minor k not positive definite
+    int nslot;
+    int store;             // write L tiles / Dinv / z to the workspace
+};
+
+__host__ __device__ inline size_t factor_smem_bytes(int nslot, int Np, int d) {
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + (d + 5) * Np + 64) + 64;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
+    FAB_DYN_SMEM(smem_raw);
+    const GpData& gd = a.gd;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int Np = gd.Np, NT = gd.NT, N = gd.N, d = gd.d;
+
+    double* slots = reinterpret_cast<double*>(smem_raw);
+    double* dinv = slots + (size_t)a.nslot * TILE_ELEMS;
+    double* zs = dinv + 512;
+    double* us = zs + (size_t)d * Np;
+    double* rvec = us + Np;
+    double* zv = rvec + Np;
+    double* accv = zv + Np;
+    double* diagv = accv + Np;
+    double* red = diagv + Np;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 64);
+    int* fail = reinterpret_cast<int*>(bar + 1);
+
+    const Hyper h = decode_hyper(gd, a.theta + (size_t)b * gd.Pk, a.yerr2[b]);
+
+    // ---- stage the observation matrix: coalesced read of X (N x D), scaled SoA copy in smem ----
+    for (int e = tid; e < N * gd.D; e += NTHREADS) {
+        const int i = e / gd.D, k = e - i * gd.D;
+        const double x = __ldg(&gd.X[e]);
+        if (k < d) zs[k * Np + i] = x * h.scale[k];
+        if (gd.family == 1 && k == d) us[i] = x;
+    }
+    for (int i = tid; i < Np; i += NTHREADS) {
+        if (i >= N) {
+            for (int k = 0; k < d; ++k) zs[k * Np + i] = 0.0;
+            us[i] = 0.0;
+        }
+        if (gd.family != 1 && i < N) us[i] = 0.0;
+        rvec[i] = (i < N) ? (__ldg(&gd.y[i]) - gd.mean) : 0.0;
+        accv[i] = 0.0;
+        zv[i] = 0.0;
+        diagv[i] = 1.0;
+    }
+    if (tid == 0) { mbar_init(bar, 1); *fail = 0; }
+    __syncthreads();
+
+    Coords co; co.zs = zs; co.us = us; co.Np = Np; co.N = N; co.d = d; co.family = gd.family;
+    TileCache tc; tc.init(slots, a.nslot, bar);
+    double* Lw = a.wk.Lw ? a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS : nullptr;
+    double* Dw = a.wk.Dinv ? a.wk.Dinv + (size_t)b * NT * 512 : nullptr;
+    const WarpTile wt = warp_tile();
+    int first_fail = 0;
+
+    for (int K = 0; K < NT; ++K) {
+        // ================= diagonal tile (K, K) =================
+        const int sd = tc.alloc(K, K, K, -1, -1, -1);
+        double* Td = tc.ptr(sd);
+        build_tile(Td, co, h, K, K);
+        __syncthreads();
+        if (K > 0) {
+            double acc[4][2][2];
+            acc_load(acc, Td, wt);
+            for (int J = 0; J < K; ++J) {
+                const int sj = tc.acquire(Lw, K, J, K, sd, -1, -1);
+                const double* Lj = tc.ptr(sj);
+                tile_mma<false, true, true>(acc, Lj, Lj, wt, 0, TS);
+            }
+            acc_store(acc, Td, wt);
+            __syncthreads();
+        }
+        {
+            const double* rhs_r = rvec + TS * K;
+            const double* rhs_a = accv + TS * K;
+            double* zl = zv + TS * K;
+            // forward substitution of the right-hand side, 8 rows at a time, overlapped with the
+            // serial 8x8 factorisations (runs on warp 1 while thread 0 factors the next block)
+            auto hook = [&](int jb) {
+                const int q = lane >> 2, p = lane & 3;
+                const int row = 8 * jb + q;
+                double s = 0.0;
+                for (int c = p; c < 8 * jb; c += 4) s = fma(Td[tix(row, c)], zl[c], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                const double v = rhs_r[row] - rhs_a[row] - s;
+                double zz = 0.0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double vc = __shfl_sync(0xffffffffu, v, 4 * c);
+                    zz = fma(dinv[64 * jb + q * 8 + c], vc, zz);     // inv8 is lower triangular (zeros above)
+                }
+                if (p == 0) zl[row] = zz;
+                __syncwarp();
+            };
+            tile_potrf(Td, dinv, fail, hook);
+        }
+        if (*fail && first_fail == 0) first_fail = TS * K + *fail;
+        if (tid < TS) diagv[TS * K + tid] = Td[tix(tid, tid)];
+        if (a.store) {
+            for (int e = tid; e < 512; e += NTHREADS) Dw[(size_t)K * 512 + e] = dinv[e];
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(K, K) * TILE_ELEMS, Td, TILE_BYTES);
+        }
+        // ================= panel tiles (I, K), I > K =================
+        for (int I = K + 1; I < NT; ++I) {
+            const int st = tc.alloc(I, K, K, sd, -1, -1);
+            double* Tt = tc.ptr(st);
+            build_tile(Tt, co, h, I, K);
+            __syncthreads();
+            if (K > 0) {
+                double acc[4][2][2];
+                acc_load(acc, Tt, wt);
+                for (int J = 0; J < K; ++J) {
+                    const int sa = tc.acquire(Lw, I, J, K, sd, st, -1);
+                    const int sb = tc.acquire(Lw, K, J, K, sd, st, sa);
+                    tile_mma<false, true, true>(acc, tc.ptr(sa), tc.ptr(sb), wt, 0, TS);
+                }
+                acc_store(acc, Tt, wt);
+                __syncthreads();
+            }
+            tile_trsm_right(Tt, Td, dinv);
+            // accv_I += L_IK z_K   (warp w: rows 8w..8w+7, lanes across columns)
+            {
+                const double z0 = zv[TS * K + lane], z1 = zv[TS * K + lane + 32];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int r = 8 * w + rr;
+                    double s = Tt[tix(r, lane)] * z0 + Tt[tix(r, lane + 32)] * z1;
+                    s = warp_sum(s);
+                    if (lane == 0) accv[TS * I + r] += s;
+                }
+            }
+            if (a.store) {
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(I, K) * TILE_ELEMS, Tt, TILE_BYTES);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- log-likelihood ----
+    double part[2] = {0.0, 0.0};
+    for (int i = tid; i < N; i += NTHREADS) {
+        part[0] += log(diagv[i]);
+        part[1] += zv[i] * zv[i];
+    }
+    block_sum<2>(part, red);
+    if (a.store) {
+        for (int i = tid; i < Np; i += NTHREADS) a.wk.zvec[(size_t)b * Np + i] = zv[i];
+    }
+    if (tid == 0) {
+        double ll = -0.5 * (N * kLog2Pi + 2.0 * part[0]) - 0.5 * part[1];
+        int inf = first_fail;
+        if (inf != 0 || !isfinite(ll)) ll = -INFINITY;      // george: non-finite -> -inf (fabolas.py:58-66)
+        a.ll[b] = ll;
+        a.info[b] = inf;
+        bulk_s2g_wait_all();
+    }
+}
+
+}  // namespace fab

@@ -1,0 +1,308 @@
+// tiles.cuh -- 64x64 FP64 tiles in shared memory and the DMMA tile algebra the GP kernels are
+// built from (tile GEMM in NT/NN/TN form, 8x8 Cholesky + inverse, in-tile factorisation, right/left
+// triangular solves against a factored diagonal tile).
+//
+// Layout: a tile is 4096 doubles (32 KB), row-major with an XOR swizzle of the column index,
+//     offset(r, c) = r * 64 + (c ^ ((r & 3) << 2)),
+// which makes both DMMA operand access patterns bank-conflict free for 8-byte loads
+//   row fragment  (lane 4g+t reads (r0+g, k0+t)) and  column fragment (lane 4g+t reads (k0+t, c0+g)),
+// keeps (c, c+1) pairs with even c adjacent (16-byte accumulator loads/stores), and keeps a tile a
+// single contiguous 32 KB blob so that one cp.async.bulk (TMA) moves it between L2/HBM and smem.
+// The same swizzled blob is the on-HBM format of the per-walker factor workspace.
+#pragma once
+#include "prims.cuh"
+
+namespace fab {
+
+constexpr int TS = 64;                 // tile edge
+constexpr int TILE_ELEMS = TS * TS;    // doubles per tile
+constexpr int TILE_BYTES = TILE_ELEMS * 8;
+constexpr int NWARPS = 8;              // all tile routines assume 256 threads
+constexpr int NTHREADS = NWARPS * 32;
+
+__device__ __forceinline__ int tix(int r, int c) { return r * TS + (c ^ ((r & 3) << 2)); }
+
+// lower-triangular tile index (I >= J)
+__host__ __device__ __forceinline__ int tri_index(int I, int J) { return I * (I + 1) / 2 + J; }
+
+// ---------------------------------------------------------------------------------------------
+// Accumulator fragment of one warp: 32 rows x 16 cols = 4 x 2 DMMA blocks.
+// acc[i][j][e] = C[m0 + 8i + g][n0 + 8j + 2t + e]
+// ---------------------------------------------------------------------------------------------
+struct WarpTile {
+    int m0, n0;   // origin of this warp's 32x16 block inside the 64x64 tile
+};
+__device__ __forceinline__ WarpTile warp_tile() {
+    const int w = threadIdx.x >> 5;
+    WarpTile wt;
+    wt.m0 = (w >> 2) * 32;
+    wt.n0 = (w & 3) * 16;
+    return wt;
+}
+
+__device__ __forceinline__ void acc_zero(double (&acc)[4][2][2]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+__device__ __forceinline__ void acc_load(double (&acc)[4][2][2], const double* C, WarpTile wt) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(&C[tix(wt.m0 + 8 * i + g, wt.n0 + 8 * j + 2 * t)]);
+            acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+        }
+}
+__device__ __forceinline__ void acc_store(const double (&acc)[4][2][2], double* C, WarpTile wt) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double2 v; v.x = acc[i][j][0]; v.y = acc[i][j][1];
+            *reinterpret_cast<double2*>(&C[tix(wt.m0 + 8 * i + g, wt.n0 + 8 * j + 2 * t)]) = v;
+        }
+}
+
+// acc += sign * opA(A) * opB(B) restricted to k in [k_lo, k_hi) (multiples of 4).
+//   opA(A)[m][k] = TA ? A[k][m] : A[m][k]        opB(B)[k][n] = TB ? B[n][k] : B[k][n]
+template <bool TA, bool TB, bool NEG>
+__device__ __forceinline__ void tile_mma(double (&acc)[4][2][2], const double* __restrict__ A,
+                                         const double* __restrict__ B, WarpTile wt, int k_lo, int k_hi) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // row-fragment addressing: (row, k0 + t) -> row*64 + ((k0 ^ sg) | t),  sg = (g & 3) << 2
+    // col-fragment addressing: (k0 + t, col) -> (k0 + t)*64 + (col ^ (t << 2))
+    const int sg = (g & 3) << 2, st = t << 2;
+    int a_off[4], b_off[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a_off[i] = TA ? (t * TS + ((wt.m0 + 8 * i + g) ^ st)) : ((wt.m0 + 8 * i + g) * TS + t);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b_off[j] = TB ? ((wt.n0 + 8 * j + g) * TS + t) : (t * TS + ((wt.n0 + 8 * j + g) ^ st));
+#pragma unroll 4
+    for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
+        const int krow = k0 ^ sg;      // swizzled column base for row fragments
+        const int kcol = k0 * TS;      // row base for column fragments
+        double a[4], b[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double v = A[a_off[i] + (TA ? kcol : krow)];
+            a[i] = NEG ? -v : v;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) b[j] = B[b_off[j] + (TB ? krow : kcol)];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 8x8 diagonal block: Cholesky + triangular inverse, done by ONE thread entirely in registers (the
+// latency-critical chain: one rsqrt per column, no cross-thread traffic).
+// Reads the lower part of block (jb, jb) of tile A, writes L (upper part of the block zeroed) back
+// and the row-major 8x8 inverse to dinv[64].  Returns the 1-based failing column or 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int potrf8_inv8(double* A, int jb, double* dinv) {
+    double a[8][8];
+    double ri[8];
+    const int o = 8 * jb;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[r][c] = (c <= r) ? A[tix(o + r, o + c)] : 0.0;
+    int fail = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double p = a[j][j];
+        if (!(p > 0.0) && fail == 0) fail = j + 1;     // catches NaN too
+        const double rinv = rsqrt(p);
+        ri[j] = rinv;
+        a[j][j] = sqrt(p);
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) a[i][j] *= rinv;
+#pragma unroll
+        for (int k = j + 1; k < 8; ++k)
+#pragma unroll
+            for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+    }
+    // inverse of the lower-triangular 8x8 block, column by column
+    double x[8][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r][c] = 0.0;
+        x[c][c] = ri[c];
+#pragma unroll
+        for (int r = c + 1; r < 8; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = c; k < r; ++k) s = fma(a[r][k], x[k][c], s);
+            x[r][c] = -s * ri[r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            A[tix(o + r, o + c)] = a[r][c];
+            dinv[r * 8 + c] = x[r][c];
+        }
+    return fail ? o + fail : 0;
+}
+
+// One DMMA-block helper: 8x8 accumulator (c0,c1) at block (bi, bj) of a tile.
+__device__ __forceinline__ void blk_load(double& c0, double& c1, const double* C, int bi, int bj) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const double2 v = *reinterpret_cast<const double2*>(&C[tix(8 * bi + g, 8 * bj + 2 * t)]);
+    c0 = v.x; c1 = v.y;
+}
+__device__ __forceinline__ void blk_store(double c0, double c1, double* C, int bi, int bj) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double2 v; v.x = c0; v.y = c1;
+    *reinterpret_cast<double2*>(&C[tix(8 * bi + g, 8 * bj + 2 * t)]) = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-tile Cholesky of a diagonal tile (lower part valid, strictly-upper 8x8 blocks must be zero).
+// On exit A = L (lower), dinv[8][64] = inverses of the eight 8x8 diagonal blocks of L.
+// `hook(jb)` is called by all threads of warp 1 while thread 0 factors block jb+1 (used to overlap
+// the forward substitution of the right-hand side with the serial chain); hook(7) runs at the end.
+// *fail (shared int) receives the first failing 1-based column within the tile, if any.
+// All 256 threads must call.  Ends with a __syncthreads().
+// ---------------------------------------------------------------------------------------------
+template <typename Hook>
+__device__ __forceinline__ void tile_potrf(double* A, double* dinv, int* fail, Hook hook) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int jb = 0; jb < 8; ++jb) {
+        // (a) serial 8x8 factor + inverse  ||  overlapped hook for the previous block
+        if (threadIdx.x == 0) {
+            const int f = potrf8_inv8(A, jb, dinv + 64 * jb);
+            if (f && *fail == 0) *fail = f;
+        } else if (w == 1 && jb > 0) {
+            hook(jb - 1);
+        }
+        __syncthreads();
+        if (jb == 7) break;
+        // (b) sub-panel: blocks (ib, jb), ib > jb:  X = A_blk * inv8^T   (one warp per block)
+        for (int ib = jb + 1 + w; ib < 8; ib += NWARPS) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += 4) {
+                const double a = A[tix(8 * ib + g, 8 * jb + k0 + t)];
+                const double b = dinv[64 * jb + g * 8 + k0 + t];      // B[k][n] = inv[n][k]
+                dmma(c0, c1, a, b);
+            }
+            blk_store(c0, c1, A, ib, jb);
+        }
+        __syncthreads();
+        // (c) trailing update inside the tile: blocks (ib, kb), jb < kb <= ib
+        const int m = 7 - jb;                 // trailing block rows
+        const int nblk = m * (m + 1) / 2;
+        for (int q = w; q < nblk; q += NWARPS) {
+            // unrank q -> (ri, rk) with rk <= ri, row-major over the lower triangle
+            int ri = 0, acc_ = 0;
+            while (acc_ + ri + 1 <= q) { acc_ += ri + 1; ++ri; }
+            const int rk = q - acc_;
+            const int ib = jb + 1 + ri, kb = jb + 1 + rk;
+            double c0, c1;
+            blk_load(c0, c1, A, ib, kb);
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += 4) {
+                const double a = -A[tix(8 * ib + g, 8 * jb + k0 + t)];
+                const double b = A[tix(8 * kb + g, 8 * jb + k0 + t)];
+                dmma(c0, c1, a, b);
+            }
+            blk_store(c0, c1, A, ib, kb);
+        }
+        __syncthreads();
+    }
+    if (w == 1) hook(7);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Right solve  X * L^T = A  (L = factored diagonal tile with its 8x8 inverses), X overwrites A.
+// Each warp owns an 8-row strip, so no block barrier is needed inside; ends with __syncthreads().
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_trsm_right(double* A, const double* __restrict__ L,
+                                                const double* __restrict__ dinv) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int s = w;                                  // strip = rows 8s .. 8s+7
+    for (int jb = 0; jb < 8; ++jb) {
+        double c0, c1;
+        blk_load(c0, c1, A, s, jb);
+        for (int kb = 0; kb < jb; ++kb) {
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += 4) {
+                const double a = -A[tix(8 * s + g, 8 * kb + k0 + t)];        // X_(s,kb)
+                const double b = L[tix(8 * jb + g, 8 * kb + k0 + t)];        // (L_(jb,kb))^T
+                dmma(c0, c1, a, b);
+            }
+        }
+        // Y = acc * inv8_jb^T : round-trip acc through the tile to turn it into an A operand
+        blk_store(c0, c1, A, s, jb);
+        __syncwarp();
+        double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0 += 4) {
+            const double a = A[tix(8 * s + g, 8 * jb + k0 + t)];
+            const double b = dinv[64 * jb + g * 8 + k0 + t];
+            dmma(y0, y1, a, b);
+        }
+        blk_store(y0, y1, A, s, jb);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Left solve  L * X = R  (X overwrites R).  Each warp owns an 8-column strip.
+// If UNIT_RHS, R is taken to be the identity (R need not be initialised) -> X = L^-1.
+// If NEG_RHS, solves L * X = -R.   Ends with __syncthreads().
+// ---------------------------------------------------------------------------------------------
+template <bool UNIT_RHS, bool NEG_RHS>
+__device__ __forceinline__ void tile_trsm_left(double* R, const double* __restrict__ L,
+                                               const double* __restrict__ dinv) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int s = w;                                  // strip = cols 8s .. 8s+7
+    for (int ib = 0; ib < 8; ++ib) {
+        double c0, c1;
+        if (UNIT_RHS) {
+            if (ib < s) {                             // X is lower triangular: zero block above the diagonal
+                blk_store(0.0, 0.0, R, ib, s);
+                continue;                             // warp-uniform
+            }
+            c0 = (ib == s && g == 2 * t) ? 1.0 : 0.0;
+            c1 = (ib == s && g == 2 * t + 1) ? 1.0 : 0.0;
+        } else {
+            blk_load(c0, c1, R, ib, s);
+            if (NEG_RHS) { c0 = -c0; c1 = -c1; }
+        }
+        for (int kb = (UNIT_RHS ? s : 0); kb < ib; ++kb) {
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += 4) {
+                const double a = -L[tix(8 * ib + g, 8 * kb + k0 + t)];       // L_(ib,kb)
+                const double b = R[tix(8 * kb + k0 + t, 8 * s + g)];         // X_(kb,s)
+                dmma(c0, c1, a, b);
+            }
+        }
+        blk_store(c0, c1, R, ib, s);
+        __syncwarp();
+        double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0 += 4) {
+            const double a = dinv[64 * ib + g * 8 + k0 + t];                 // inv8_ib
+            const double b = R[tix(8 * ib + k0 + t, 8 * s + g)];
+            dmma(y0, y1, a, b);
+        }
+        blk_store(y0, y1, R, ib, s);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+}  // namespace fab

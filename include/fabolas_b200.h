@@ -1,0 +1,81 @@
+/* fabolas_b200.h -- C ABI of the B200-native FABOLAS GP inner-loop engine (libfabolas_b200.so).
+ *
+ * The reference (rickie95/fabolas) is pure Python and has no FFI: the seam this library plugs
+ * into is the set of Python objects its hot path calls (george's GP/kernels, emcee's log-prob
+ * callback, epmgp.joint_min, acquisitions.information_gain).  Each entry point below names the
+ * reference interface it replaces (file:line in /root/reference); the ctypes binding a maintainer
+ * would add is shown in INTEGRATION.md and implemented in fabolas_b200/_capi.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to FP64 (double) / int32 data unless stated otherwise;
+ *     the caller (PyTorch in this repo) owns all input and output buffers;
+ *   - all work is enqueued on the stream given at fab_ctx_create; no hidden synchronisation;
+ *   - functions return 0 on success or a negative FAB_E* code and never throw or abort;
+ *     numerical failure of one item is DATA (info[b] > 0, ll[b] = -inf), mirroring the reference's
+ *     `try: gp.compute(...) except: return -np.inf` (fabolas.py:58-64, entropy_search.py:72-75);
+ *   - a fab_ctx owns only scratch workspaces; it is bound to one device and is not thread-safe.
+ *
+ * Kernel families (george parameter order, log space)
+ *   FAB_FAMILY_M52       theta = [log_c0, log_M_0 .. log_M_{d-1}]                       d = D
+ *       k = amp * m52(r2),  amp = amp_mult * exp(log_c0),  r2 = sum_k (x_k - x'_k)^2 / M_k
+ *       (entropy_search.py:32-36, 113-117)
+ *   FAB_FAMILY_M52_BASIS theta = [log_c0, log_M_0 .. log_M_{d-1}, log_gamma2, log_cb]   d = D - 1
+ *       k = amp * m52(r2) * (u u' / gamma2 + cb),  u = column d of X
+ *       (fabolas.py:81-97, 153-169, 227-243)
+ */
+#ifndef FABOLAS_B200_H
+#define FABOLAS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fab_ctx fab_ctx;
+
+enum {
+    FAB_OK = 0,
+    FAB_EINVAL = -1,       /* bad argument (shape, family, null pointer) */
+    FAB_ENOMEM = -2,       /* workspace allocation failed */
+    FAB_ECUDA = -3,        /* CUDA runtime error; see fab_last_error */
+    FAB_ESTATE = -4,       /* call order violated (e.g. predict before factorize) */
+    FAB_EUNSUPPORTED = -5  /* shape outside what this build handles */
+};
+enum { FAB_FAMILY_M52 = 0, FAB_FAMILY_M52_BASIS = 1 };
+
+/* library / context ------------------------------------------------------------------------- */
+int fab_version(void);
+int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream);
+int fab_ctx_destroy(fab_ctx* ctx);
+const char* fab_last_error(const fab_ctx* ctx);
+
+/* Observations of one GP problem: X is N x D row-major, y has N entries, `mean` is the constant
+ * mean george's GP(kernel, mean=np.mean(y)) subtracts (fabolas.py:99,171; entropy_search.py:37,118).
+ * `amp_mult` is the number of axes george sums the amplitude ConstantKernel over (ndim).
+ * The data are copied into the context.                                                        */
+int fab_gp_set_data(fab_ctx* ctx, int family, const double* X, int N, int D, const double* y,
+                    double mean, double amp_mult);
+
+/* Batched marginal log-likelihood (+ gradient): replaces, for B hyper-parameter rows at once,
+ *   gp.kernel.set_parameter_vector(theta); gp.compute(X, sqrt(yerr2)); gp.log_likelihood(y, quiet=True)
+ * (fabolas.py:57-66, entropy_search.py:71-77) and george's grad_log_likelihood convention.
+ *   theta  B x Pk   (Pk = d+1 or d+3)          yerr2  B   (added to the diagonal with 1.25e-12)
+ *   ll     B        (-inf where not positive definite)
+ *   grad   B x (Pk+1) or NULL: d ll / d theta_k, last column d ll / d yerr2
+ *   info   B        0, or the 1-based index of the failing leading minor                        */
+int fab_gp_loglik_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll,
+                        double* grad, int* info);
+
+/* Factorise B models and keep them resident in the context for prediction / acquisition calls:
+ * replaces the per-hyper-sample model construction `GP(kernel, mean); regressor.compute(x, yerr)`
+ * (fabolas.py:171-176, 245-248; entropy_search.py:118-119).  Also returns ll/info like loglik.   */
+int fab_gp_factorize_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll,
+                           int* info);
+
+/* Debug / test access: copy the dense lower Cholesky factor of walker b (N x N row-major, device)
+ * out of the tiled workspace left by the last fab_gp_loglik_batch(grad != NULL) / factorize call. */
+int fab_gp_debug_get_factor(fab_ctx* ctx, int b, double* L_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FABOLAS_B200_H */
