@@ -1,6 +1,7 @@
 // api.cu -- C ABI (include/fabolas_b200.h): context, workspaces, launch logic.
 #include "../../include/fabolas_b200.h"
 #include "gp_factor.cuh"
+#include "gp_grad.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -20,9 +21,10 @@ struct fab_ctx {
     double* dy = nullptr; size_t capy = 0;
     // workspaces
     GpWork wk{};
-    size_t capL = 0, capD = 0, capZ = 0;
+    size_t capL = 0, capD = 0, capZ = 0, capA = 0;
     int wsB = 0;            // walkers the factor workspace currently describes
     bool factored = false;
+    bool inverted = false;  // workspace holds W = L^-1 (and alpha) instead of L
     int smem_optin = 232448;
 };
 
@@ -87,6 +89,7 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess && v > 0)
         c->smem_optin = v;
     cudaFuncSetAttribute(gp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(gp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
 #endif
     *out = c;
     return FAB_OK;
@@ -140,6 +143,7 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
         if ((rc = ensure(c, &c->wk.Lw, &c->capL, (size_t)B * ntiles * TILE_ELEMS)) != FAB_OK) return rc;
         if ((rc = ensure(c, &c->wk.Dinv, &c->capD, (size_t)B * gd.NT * 512)) != FAB_OK) return rc;
         if ((rc = ensure(c, &c->wk.zvec, &c->capZ, (size_t)B * gd.Np)) != FAB_OK) return rc;
+        if ((rc = ensure(c, &c->wk.alpha, &c->capA, (size_t)B * gd.Np)) != FAB_OK) return rc;
     }
     FactorArgs a;
     a.gd = gd; a.wk = c->wk;
@@ -149,7 +153,23 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
     const size_t smem = factor_smem_bytes(nslot, gd.Np, gd.d);
     FAB_LAUNCH(gp_factor_kernel, B, NTHREADS, smem, c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
-    if (need_ws) { c->wsB = B; c->factored = true; }
+    if (need_ws) { c->wsB = B; c->factored = true; c->inverted = false; }
+    return FAB_OK;
+}
+
+// W = L^-1 in place + alpha (+ gradient when grad != null); needs the workspace of launch_factor(store).
+static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int B, double* grad, const int* info) {
+    const GpData& gd = c->gd;
+    const int ntiles = gd.NT * (gd.NT + 1) / 2;
+    int nslot = MAX_SLOTS;
+    while (nslot > 0 && grad_smem_bytes(nslot, gd.Np, gd.d) > (size_t)c->smem_optin) --nslot;
+    if (nslot > 2 * ntiles) nslot = 2 * ntiles;
+    if (nslot < 4 && nslot < 2 * ntiles) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA gradient kernel");
+    GradArgs a;
+    a.gd = gd; a.wk = c->wk; a.theta = theta; a.yerr2 = yerr2; a.grad = grad; a.info = info; a.nslot = nslot;
+    FAB_LAUNCH(gp_grad_kernel, B, NTHREADS, grad_smem_bytes(nslot, gd.Np, gd.d), c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    c->inverted = true;
     return FAB_OK;
 }
 
@@ -161,7 +181,7 @@ int fab_gp_loglik_batch(fab_ctx* c, const double* theta, const double* yerr2, in
     FAB_CUDA(c, cudaSetDevice(c->device));
     int rc = launch_factor(c, theta, yerr2, B, ll, info, grad != nullptr);
     if (rc != FAB_OK) return rc;
-    if (grad) return fail(c, FAB_EUNSUPPORTED, "gradient kernel not built yet");
+    if (grad) return launch_grad(c, theta, yerr2, B, grad, info);
     return FAB_OK;
 }
 
@@ -175,7 +195,8 @@ int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2,
 
 int fab_gp_debug_get_factor(fab_ctx* c, int b, double* L_out) {
     if (!c || !L_out) return FAB_EINVAL;
-    if (!c->factored || b < 0 || b >= c->wsB) return fail(c, FAB_ESTATE, "no factor workspace for this walker");
+    if (!c->factored || c->inverted || b < 0 || b >= c->wsB)
+        return fail(c, FAB_ESTATE, "no Cholesky factor in the workspace for this walker");
     const GpData& gd = c->gd;
     const int ntiles = gd.NT * (gd.NT + 1) / 2;
     FAB_LAUNCH(untile_kernel, gd.N, 128, 0, c->stream, c->wk.Lw + (size_t)b * ntiles * TILE_ELEMS, L_out, gd.N,

@@ -110,8 +110,13 @@ __device__ __forceinline__ void build_tile(double* tile, const Coords& c, const 
 // ---------------------------------------------------------------------------------------------
 // Shared-memory tile cache.  Every thread keeps an identical copy of the (tiny) directory in
 // registers and runs the same deterministic policy, so no communication is needed to agree on
-// hits, victims and slots.  Tiles are identified by (I << 16) | J.
+// hits, victims and slots.  Tile ids: (kind << 30) | (I << 16) | J, kind 0 = L tile, 1 = W = L^-1.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tile_id(int kind, int I, int J) { return (kind << 30) | (I << 16) | J; }
+__device__ __forceinline__ int id_row(int id) { return (id >> 16) & 0x3fff; }
+__device__ __forceinline__ int id_col(int id) { return id & 0xffff; }
+__device__ __forceinline__ int id_kind(int id) { return (id >> 30) & 1; }
+
 struct TileCache {
     int id[MAX_SLOTS];
     int stamp[MAX_SLOTS];
@@ -126,6 +131,11 @@ struct TileCache {
         for (int s = 0; s < MAX_SLOTS; ++s) { id[s] = -1; stamp[s] = 0; }
     }
     __device__ __forceinline__ double* ptr(int s) const { return base + (size_t)s * TILE_ELEMS; }
+    __device__ __forceinline__ void touch(int s) {
+        ++clock;
+#pragma unroll
+        for (int q = 0; q < MAX_SLOTS; ++q) if (q == s) stamp[q] = clock;
+    }
     __device__ __forceinline__ int find(int tid_) {
         int f = -1;
 #pragma unroll
@@ -133,21 +143,17 @@ struct TileCache {
         if (f >= 0) touch(f);
         return f;
     }
-    __device__ __forceinline__ void touch(int s) {
-        ++clock;
-#pragma unroll
-        for (int q = 0; q < MAX_SLOTS; ++q) if (q == s) stamp[q] = clock;
-    }
-    // Pick a slot to (re)use: free first, then dead (tile row < dead_below), then least recently
-    // used; slots p0/p1/p2 are pinned.
-    __device__ __forceinline__ int victim(int dead_below, int p0, int p1, int p2) {
+    // Pick a slot to (re)use: free first, then dead (per the caller's predicate), then least
+    // recently used; slots p0/p1/p2 are pinned.
+    template <typename Dead>
+    __device__ __forceinline__ int victim(Dead dead, int p0, int p1, int p2) {
         int best = -1, best_score = 0x7fffffff;
 #pragma unroll
         for (int s = 0; s < MAX_SLOTS; ++s) {
             if (s >= nslot || s == p0 || s == p1 || s == p2) continue;
             int score;
             if (id[s] < 0) score = -2000000000;
-            else if ((id[s] >> 16) < dead_below) score = -1000000000 + stamp[s];
+            else if (dead(id[s])) score = -1000000000 + stamp[s];
             else score = stamp[s];
             if (score < best_score) { best_score = score; best = s; }
         }
@@ -160,27 +166,28 @@ struct TileCache {
     }
     // Reserve a slot for a tile that is about to be produced in shared memory.  Contains a block
     // barrier (orders earlier readers of the victim and drains its pending bulk store).
-    __device__ __forceinline__ int alloc(int I, int J, int dead_below, int p0, int p1, int p2) {
-        const int s = victim(dead_below, p0, p1, p2);
+    template <typename Dead>
+    __device__ __forceinline__ int alloc(int tid_, Dead dead, int p0, int p1, int p2) {
+        const int s = victim(dead, p0, p1, p2);
         if (threadIdx.x == 0) bulk_s2g_wait_read();
         __syncthreads();
-        set(s, (I << 16) | J);
+        set(s, tid_);
         return s;
     }
-    // Make tile (I, J) resident, loading it from the HBM/L2 workspace on a miss (TMA bulk copy).
-    __device__ __forceinline__ int acquire(const double* Lw_walker, int I, int J, int dead_below,
-                                           int p0, int p1, int p2) {
-        int s = find((I << 16) | J);
+    // Make a tile resident, loading it from the HBM/L2 workspace on a miss (TMA bulk copy).
+    template <typename Dead>
+    __device__ __forceinline__ int acquire(const double* Lw_walker, int tid_, Dead dead, int p0, int p1, int p2) {
+        int s = find(tid_);
         if (s >= 0) return s;
-        s = victim(dead_below, p0, p1, p2);
+        s = victim(dead, p0, p1, p2);
         __syncthreads();                       // nobody may still be reading the victim
         if (threadIdx.x == 0) {
             bulk_s2g_wait_all();               // write-through stores must have landed
-            bulk_g2s(ptr(s), Lw_walker + (size_t)tri_index(I, J) * TILE_ELEMS, TILE_BYTES, bar);
+            bulk_g2s(ptr(s), Lw_walker + (size_t)tri_index(id_row(tid_), id_col(tid_)) * TILE_ELEMS, TILE_BYTES, bar);
         }
         mbar_wait(bar, phase & 1u);
         ++phase;
-        set(s, (I << 16) | J);
+        set(s, tid_);
         return s;
     }
 };

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
 
     for (int K = 0; K < NT; ++K) {
         // ================= diagonal tile (K, K) =================
-        const int sd = tc.alloc(K, K, K, -1, -1, -1);
+        auto dead = [K](int id) { return id_row(id) < K; };   // rows above the current block column are done
+        const int sd = tc.alloc(tile_id(0, K, K), dead, -1, -1, -1);
         double* Td = tc.ptr(sd);
         build_tile(Td, co, h, K, K);
         __syncthreads();
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             double acc[4][2][2];
             acc_load(acc, Td, wt);
             for (int J = 0; J < K; ++J) {
-                const int sj = tc.acquire(Lw, K, J, K, sd, -1, -1);
+                const int sj = tc.acquire(Lw, tile_id(0, K, J), dead, sd, -1, -1);
                 const double* Lj = tc.ptr(sj);
                 tile_mma<false, true, true>(acc, Lj, Lj, wt, 0, TS);
             }
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
         }
         // ================= panel tiles (I, K), I > K =================
         for (int I = K + 1; I < NT; ++I) {
-            const int st = tc.alloc(I, K, K, sd, -1, -1);
+            const int st = tc.alloc(tile_id(0, I, K), dead, sd, -1, -1);
             double* Tt = tc.ptr(st);
             build_tile(Tt, co, h, I, K);
             __syncthreads();
@@ -139,8 +140,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                 double acc[4][2][2];
                 acc_load(acc, Tt, wt);
                 for (int J = 0; J < K; ++J) {
-                    const int sa = tc.acquire(Lw, I, J, K, sd, st, -1);
-                    const int sb = tc.acquire(Lw, K, J, K, sd, st, sa);
+                    const int sa = tc.acquire(Lw, tile_id(0, I, J), dead, sd, st, -1);
+                    const int sb = tc.acquire(Lw, tile_id(0, K, J), dead, sd, st, sa);
                     tile_mma<false, true, true>(acc, tc.ptr(sa), tc.ptr(sb), wt, 0, TS);
                 }
                 acc_store(acc, Tt, wt);

@@ -1,0 +1,218 @@
+// gp_grad.cuh -- kernel B: in-place triangular inverse W = L^-1, alpha = K^-1 r, and the gradient of
+// the marginal log-likelihood in george's grad_log_likelihood convention:
+//     g_k = 0.5 * sum_ij (alpha_i alpha_j - K^-1_ij) dK_ij / dtheta_k ,   K^-1 = W^T W
+// One CTA per walker, run after gp_factor_kernel (which left L, the 8x8 inverses and z in the
+// workspace).  K^-1 is never stored: each 64x64 tile of W^T W is accumulated in DMMA registers
+// and contracted on the spot with dK regenerated from the staged observations.
+//   phase 1 (trtri): column by column, W_JJ = L_JJ^-1, W_IJ = -L_II^-1 sum_{J<=k<I} L_Ik W_kJ,
+//                    written over L in the workspace; alpha_J = sum_I W_IJ^T z_I
+//   phase 2 (lauum + contraction): (K^-1)_IJ = sum_{k>=I} W_kI^T W_kJ
+#pragma once
+#include "gp_common.cuh"
+
+namespace fab {
+
+struct GradArgs {
+    GpData gd;
+    GpWork wk;
+    const double* theta;   // B x Pk
+    const double* yerr2;   // B
+    double* grad;          // B x (Pk + 1) or null (then only W and alpha are produced)
+    const int* info;       // B (from the factor kernel); walkers with info != 0 get NaN gradients
+    int nslot;
+};
+
+__host__ __device__ inline size_t grad_smem_bytes(int nslot, int Np, int d) {
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + (d + 3) * Np + 512 + 128) + 64;
+}
+
+// alpha_J += T^T z_I for one 64x64 tile T (rows = block I, cols = block J).  Two barriers.
+__device__ __forceinline__ void tile_matvec_t(const double* T, const double* zI, double* alphaJ, double* part) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        const int r = 8 * w + rr;
+        const double zr = zI[r];
+        s0 = fma(T[tix(r, lane)], zr, s0);
+        s1 = fma(T[tix(r, lane + 32)], zr, s1);
+    }
+    part[w * 64 + lane] = s0;
+    part[w * 64 + lane + 32] = s1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < NWARPS; ++q) s += part[q * 64 + threadIdx.x];
+        alphaJ[threadIdx.x] += s;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
+    FAB_DYN_SMEM(smem_raw);
+    const GpData& gd = a.gd;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int Np = gd.Np, NT = gd.NT, N = gd.N, d = gd.d, Pk = gd.Pk;
+
+    double* slots = reinterpret_cast<double*>(smem_raw);
+    double* dinv = slots + (size_t)a.nslot * TILE_ELEMS;
+    double* zs = dinv + 512;
+    double* us = zs + (size_t)d * Np;
+    double* zv = us + Np;
+    double* al = zv + Np;
+    double* part = al + Np;            // 512
+    double* red = part + 512;          // 128
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 128);
+
+    const Hyper h = decode_hyper(gd, a.theta + (size_t)b * Pk, a.yerr2[b]);
+    double* Lw = a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS;
+    const double* Dw = a.wk.Dinv + (size_t)b * NT * 512;
+
+    if (a.info[b] != 0) {      // not positive definite: no factor to differentiate
+        if (a.grad) for (int k = tid; k <= Pk; k += NTHREADS) a.grad[(size_t)b * (Pk + 1) + k] = NAN;
+        return;
+    }
+
+    for (int e = tid; e < N * gd.D; e += NTHREADS) {
+        const int i = e / gd.D, k = e - i * gd.D;
+        const double x = __ldg(&gd.X[e]);
+        if (k < d) zs[k * Np + i] = x * h.scale[k];
+        if (gd.family == 1 && k == d) us[i] = x;
+    }
+    for (int i = tid; i < Np; i += NTHREADS) {
+        if (i >= N) {
+            for (int k = 0; k < d; ++k) zs[k * Np + i] = 0.0;
+            us[i] = 0.0;
+        }
+        if (gd.family != 1 && i < N) us[i] = 0.0;
+        zv[i] = a.wk.zvec[(size_t)b * Np + i];
+        al[i] = 0.0;
+    }
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+
+    TileCache tc; tc.init(slots, a.nslot, bar);
+    const WarpTile wt = warp_tile();
+
+    // ======================= phase 1: W = L^-1 in place, alpha = W^T z =======================
+    for (int J = 0; J < NT; ++J) {
+        // W tiles of earlier columns are not needed again in this phase
+        auto dead = [J](int id) { return id_kind(id) == 1 && id_col(id) < J; };
+        {
+            const int sl = tc.acquire(Lw, tile_id(0, J, J), dead, -1, -1, -1);
+            const int sw = tc.alloc(tile_id(1, J, J), dead, sl, -1, -1);
+            for (int e = tid; e < 512; e += NTHREADS) dinv[e] = Dw[(size_t)J * 512 + e];
+            __syncthreads();
+            tile_trsm_left<true, false>(tc.ptr(sw), tc.ptr(sl), dinv);
+            tile_matvec_t(tc.ptr(sw), zv + TS * J, al + TS * J, part);
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(J, J) * TILE_ELEMS, tc.ptr(sw), TILE_BYTES);
+        }
+        for (int I = J + 1; I < NT; ++I) {
+            const int ss = tc.alloc(tile_id(1, I, J), dead, -1, -1, -1);
+            double acc[4][2][2];
+            acc_zero(acc);
+            for (int k = J; k < I; ++k) {
+                const int sa = tc.acquire(Lw, tile_id(0, I, k), dead, ss, -1, -1);
+                const int sb = tc.acquire(Lw, tile_id(1, k, J), dead, ss, sa, -1);
+                // W_JJ is lower triangular: rows k' < n contribute nothing
+                tile_mma<false, false, false>(acc, tc.ptr(sa), tc.ptr(sb), wt, (k == J) ? wt.n0 : 0, TS);
+            }
+            acc_store(acc, tc.ptr(ss), wt);
+            const int sl = tc.acquire(Lw, tile_id(0, I, I), dead, ss, -1, -1);
+            for (int e = tid; e < 512; e += NTHREADS) dinv[e] = Dw[(size_t)I * 512 + e];
+            __syncthreads();
+            tile_trsm_left<false, true>(tc.ptr(ss), tc.ptr(sl), dinv);
+            tile_matvec_t(tc.ptr(ss), zv + TS * I, al + TS * J, part);
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(I, J) * TILE_ELEMS, tc.ptr(ss), TILE_BYTES);
+        }
+    }
+    __syncthreads();
+    if (a.wk.alpha) for (int i = tid; i < Np; i += NTHREADS) a.wk.alpha[(size_t)b * Np + i] = al[i];
+    if (!a.grad) {
+        if (tid == 0) bulk_s2g_wait_all();
+        return;
+    }
+
+    // ======================= phase 2: K^-1 tiles + gradient contraction =======================
+    // accumulators: [0] log_c0, [1..d] log_M_k, [d+1] log_gamma2, [d+2] log_cb, [MAX_PK] yerr2
+    double gacc[MAX_PK + 1];
+#pragma unroll
+    for (int k = 0; k <= MAX_PK; ++k) gacc[k] = 0.0;
+
+    for (int J = 0; J < NT; ++J) {
+        auto dead = [J](int id) { return id_kind(id) == 0 || id_col(id) < J; };
+        for (int I = J; I < NT; ++I) {
+            double acc[4][2][2];
+            acc_zero(acc);
+            for (int k = I; k < NT; ++k) {
+                const int sa = tc.acquire(Lw, tile_id(1, k, I), dead, -1, -1, -1);
+                const int sb = tc.acquire(Lw, tile_id(1, k, J), dead, sa, -1, -1);
+                // W_II is lower triangular: (W_II)[k'][m] = 0 for k' < m
+                tile_mma<true, false, false>(acc, tc.ptr(sa), tc.ptr(sb), wt, (k == I) ? wt.m0 : 0, TS);
+            }
+            // contraction with dK over this warp's 32 x 16 fragment
+            const double wgt = (I == J) ? 1.0 : 2.0;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const int gi = TS * I + wt.m0 + 8 * i4 + g;
+#pragma unroll
+                for (int j2 = 0; j2 < 2; ++j2) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int gj = TS * J + wt.n0 + 8 * j2 + 2 * t + e;
+                        if (gi < N && gj < N) {
+                            const double wij = wgt * (al[gi] * al[gj] - acc[i4][j2][e]);
+                            double r2 = 0.0;
+                            double tk[MAX_D];
+#pragma unroll
+                            for (int k = 0; k < MAX_D; ++k) {
+                                if (k < d) {
+                                    const double dz = zs[k * Np + gi] - zs[k * Np + gj];
+                                    tk[k] = dz * dz;
+                                    r2 += tk[k];
+                                } else {
+                                    tk[k] = 0.0;
+                                }
+                            }
+                            double m, gf;
+                            matern52(r2, m, gf);
+                            const double uu = us[gi] * us[gj] * h.inv_g2;
+                            const double beta = (gd.family == 1) ? (uu + h.cb) : 1.0;
+                            const double wa = wij * h.amp;
+                            gacc[0] = fma(wa * m, beta, gacc[0]);
+                            const double wg = wa * beta * gf;
+#pragma unroll
+                            for (int k = 0; k < MAX_D; ++k) gacc[1 + k] = fma(wg, tk[k], gacc[1 + k]);
+                            if (gd.family == 1) {
+                                gacc[MAX_D + 1] = fma(-wa * m, uu, gacc[MAX_D + 1]);
+                                gacc[MAX_D + 2] = fma(wa * m, h.cb, gacc[MAX_D + 2]);
+                            }
+                            if (gi == gj) gacc[MAX_PK] += wij;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    block_sum<MAX_PK + 1>(gacc, red);
+    if (tid == 0) {
+        double* go = a.grad + (size_t)b * (Pk + 1);
+        go[0] = 0.5 * gacc[0];
+        for (int k = 0; k < d; ++k) go[1 + k] = 0.5 * gacc[1 + k];
+        if (gd.family == 1) {
+            go[1 + d] = 0.5 * gacc[MAX_D + 1];
+            go[2 + d] = 0.5 * gacc[MAX_D + 2];
+        }
+        go[Pk] = 0.5 * gacc[MAX_PK];
+        bulk_s2g_wait_all();
+    }
+}
+
+}  // namespace fab
