@@ -32,6 +32,8 @@ SIGNATURES = {
     "fab_ctx_create": (_c_int, [ctypes.POINTER(_vp), _c_int, _vp]),
     "fab_ctx_destroy": (_c_int, [_vp]),
     "fab_last_error": (ctypes.c_char_p, [_vp]),
+    "fab_ctx_set_timing": (_c_int, [_vp, _c_int]),
+    "fab_ctx_get_timing": (_c_int, [_vp, ctypes.POINTER(_c_dbl), _c_int]),
     "fab_gp_set_data": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_dbl, _c_dbl]),
     "fab_gp_loglik_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
     "fab_gp_factorize_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
@@ -116,6 +118,17 @@ class Engine:
 
     def empty(self, *shape, dtype=torch.float64) -> torch.Tensor:
         return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def set_timing(self, enable: bool):
+        self._check(self.lib.fab_ctx_set_timing(self._ctx, int(enable)), "fab_ctx_set_timing")
+
+    def get_timing(self):
+        """Durations (ms) of the kernels launched by the most recent batched call."""
+        buf = (_c_dbl * 4)()
+        n = self.lib.fab_ctx_get_timing(self._ctx, buf, 4)
+        if n < 0:
+            self._check(n, "fab_ctx_get_timing")
+        return [buf[i] for i in range(n)]
 
     # ------------------------------------------------------------------------------------------
     def set_data(self, family: int, X, y, mean: float, amp_mult: Optional[float] = None):

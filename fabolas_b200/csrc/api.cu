@@ -26,6 +26,10 @@ struct fab_ctx {
     bool factored = false;
     bool inverted = false;  // workspace holds W = L^-1 (and alpha) instead of L
     int smem_optin = 232448;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int ev_used = 0;        // number of intervals recorded by the last call
 };
 
 namespace {
@@ -99,9 +103,38 @@ int fab_ctx_destroy(fab_ctx* c) {
     if (!c) return FAB_EINVAL;
     cudaSetDevice(c->device);
     cudaFree(c->dX); cudaFree(c->dy);
+#ifndef FAB_CUSIM
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+#endif
     cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha);
     delete c;
     return FAB_OK;
+}
+
+int fab_ctx_set_timing(fab_ctx* c, int enable) {
+    if (!c) return FAB_EINVAL;
+#ifndef FAB_CUSIM
+    if (enable && !c->ev[0])
+        for (int i = 0; i < 4; ++i) FAB_CUDA(c, cudaEventCreate(&c->ev[i]));
+#endif
+    c->timing = enable != 0;
+    c->ev_used = 0;
+    return FAB_OK;
+}
+
+int fab_ctx_get_timing(fab_ctx* c, double* ms_out, int n) {
+    if (!c || !ms_out) return FAB_EINVAL;
+    for (int i = 0; i < n; ++i) ms_out[i] = 0.0;
+#ifndef FAB_CUSIM
+    if (!c->timing || c->ev_used == 0) return fail(c, FAB_ESTATE, "no timed launch recorded");
+    FAB_CUDA(c, cudaEventSynchronize(c->ev[c->ev_used]));
+    for (int i = 0; i < c->ev_used && i < n; ++i) {
+        float ms = 0.f;
+        FAB_CUDA(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+        ms_out[i] = ms;
+    }
+#endif
+    return c->ev_used;
 }
 
 const char* fab_last_error(const fab_ctx* c) { return c ? c->err.c_str() : "null context"; }
@@ -151,8 +184,10 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
     a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info;
     a.nslot = nslot; a.store = need_ws ? 1 : 0;
     const size_t smem = factor_smem_bytes(nslot, gd.Np, gd.d);
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     FAB_LAUNCH(gp_factor_kernel, B, NTHREADS, smem, c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
     if (need_ws) { c->wsB = B; c->factored = true; c->inverted = false; }
     return FAB_OK;
 }
@@ -169,6 +204,7 @@ static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int
     a.gd = gd; a.wk = c->wk; a.theta = theta; a.yerr2 = yerr2; a.grad = grad; a.info = info; a.nslot = nslot;
     FAB_LAUNCH(gp_grad_kernel, B, NTHREADS, grad_smem_bytes(nslot, gd.Np, gd.d), c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[2], c->stream)); c->ev_used = 2; }
     c->inverted = true;
     return FAB_OK;
 }

@@ -48,6 +48,13 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream);
 int fab_ctx_destroy(fab_ctx* ctx);
 const char* fab_last_error(const fab_ctx* ctx);
 
+/* Optional per-kernel timing for benchmarks: when enabled, every batched call records CUDA events
+ * around each of its kernel launches on the context's stream.  fab_ctx_get_timing synchronises on
+ * the last event and writes the durations (ms) of the kernels of the most recent call, in launch
+ * order (loglik: [factor, gradient]); returns the number of intervals or a negative code.        */
+int fab_ctx_set_timing(fab_ctx* ctx, int enable);
+int fab_ctx_get_timing(fab_ctx* ctx, double* ms_out, int n);
+
 /* Observations of one GP problem: X is N x D row-major, y has N entries, `mean` is the constant
  * mean george's GP(kernel, mean=np.mean(y)) subtracts (fabolas.py:99,171; entropy_search.py:37,118).
  * `amp_mult` is the number of axes george sums the amplitude ConstantKernel over (ndim).

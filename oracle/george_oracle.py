@@ -231,8 +231,8 @@ class GP:
         alpha = self._compute_alpha(y)
         Kinv = self.apply_inverse(np.eye(self._x.shape[0]))
         W = np.outer(alpha, alpha) - Kinv
-        dK = self.kernel.get_gradient(self._x)
-        g = 0.5 * np.einsum("ijk,ij->k", dK, W)
+        dK = self.kernel._value_and_grads(self._x, self._x)[1]          # list of N x N arrays
+        g = 0.5 * np.array([np.vdot(dk, W) for dk in dK])               # = 0.5 einsum('ijk,ij->k')
         if with_yerr2:
             g = np.append(g, 0.5 * np.trace(W))
         return g
