@@ -37,6 +37,9 @@ SIGNATURES = {
     "fab_gp_set_data": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_dbl, _c_dbl]),
     "fab_gp_loglik_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
     "fab_gp_factorize_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
+    "fab_gp_fit_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
+    "fab_gp_predict_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp]),
+    "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
 }
 
@@ -176,6 +179,53 @@ class Engine:
                     "fab_gp_factorize_batch")
         self.B = B
         return ll, info
+
+    def fit(self, theta, yerr2):
+        """Make B models resident (factor, inverse factor, alpha).  Returns (ll, info)."""
+        theta, yerr2 = self._theta(theta, yerr2)
+        B = theta.shape[0]
+        ll = self.empty(B)
+        info = self.empty(B, dtype=torch.int32)
+        self._check(self.lib.fab_gp_fit_batch(self._ctx, _ptr(theta), _ptr(yerr2), B, _ptr(ll), _ptr(info)),
+                    "fab_gp_fit_batch")
+        self.B = B
+        return ll, info
+
+    def predict(self, T, want_var: bool = True, want_cov: bool = False):
+        """mu (B, M) [, var (B, M)] [, cov (B, M, M)] of every resident model at the rows of T."""
+        T = self.tensor(T)
+        if T.dim() == 1:
+            T = T[None]
+        if T.shape[1] != self.D:
+            raise ValueError(f"T must have {self.D} columns")
+        M = T.shape[0]
+        mu = self.empty(self.B, M)
+        var = self.empty(self.B, M) if want_var else None
+        cov = self.empty(self.B, M, M) if want_cov else None
+        self._check(self.lib.fab_gp_predict_batch(self._ctx, _ptr(T), M, _ptr(mu), _ptr(var), _ptr(cov)),
+                    "fab_gp_predict_batch")
+        out = [mu]
+        if want_var:
+            out.append(var)
+        if want_cov:
+            out.append(cov)
+        return tuple(out)
+
+    def expected_improvement(self, mu, var, y_max, xi: float = 0.0, want_ei: bool = True):
+        """EI (B, M), best value (B,), argmax (B,) for predictive moments mu/var (B, M)."""
+        mu, var = self.tensor(mu), self.tensor(var)
+        if mu.dim() == 1:
+            mu, var = mu[None], var[None]
+        B, M = mu.shape
+        y_max = self.tensor(y_max).reshape(-1)
+        if y_max.numel() == 1 and B > 1:
+            y_max = y_max.expand(B).contiguous()
+        ei = self.empty(B, M) if want_ei else None
+        bv = self.empty(B)
+        bi = self.empty(B, dtype=torch.int64)
+        self._check(self.lib.fab_ei_batch(self._ctx, _ptr(mu), _ptr(var), B, M, _ptr(y_max), float(xi), _ptr(ei),
+                                          _ptr(bv), _ptr(bi)), "fab_ei_batch")
+        return ei, bv, bi
 
     def debug_factor(self, b: int) -> torch.Tensor:
         L = self.empty(self.N, self.N)

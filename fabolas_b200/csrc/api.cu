@@ -2,6 +2,7 @@
 #include "../../include/fabolas_b200.h"
 #include "gp_factor.cuh"
 #include "gp_grad.cuh"
+#include "gp_predict.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -22,6 +23,10 @@ struct fab_ctx {
     // workspaces
     GpWork wk{};
     size_t capL = 0, capD = 0, capZ = 0, capA = 0;
+    double* dTheta = nullptr; size_t capT = 0;   // hyper-parameters of the resident models
+    double* dYerr2 = nullptr; size_t capY = 0;
+    int* dInfo = nullptr; size_t capI = 0;
+    bool resident = false;  // factorize_batch completed: W, alpha, theta resident
     int wsB = 0;            // walkers the factor workspace currently describes
     bool factored = false;
     bool inverted = false;  // workspace holds W = L^-1 (and alpha) instead of L
@@ -94,6 +99,8 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
         c->smem_optin = v;
     cudaFuncSetAttribute(gp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(gp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(gp_predict_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(gp_predict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
 #endif
     *out = c;
     return FAB_OK;
@@ -102,7 +109,7 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
 int fab_ctx_destroy(fab_ctx* c) {
     if (!c) return FAB_EINVAL;
     cudaSetDevice(c->device);
-    cudaFree(c->dX); cudaFree(c->dy);
+    cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dTheta); cudaFree(c->dYerr2); cudaFree(c->dInfo);
 #ifndef FAB_CUSIM
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 #endif
@@ -158,6 +165,7 @@ int fab_gp_set_data(fab_ctx* c, int family, const double* X, int N, int D, const
     gd.Pk = pk_of(gd);
     c->has_data = true;
     c->factored = false;
+    c->resident = false;
     return FAB_OK;
 }
 
@@ -188,6 +196,7 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
     FAB_LAUNCH(gp_factor_kernel, B, NTHREADS, smem, c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
+    c->resident = false;
     if (need_ws) { c->wsB = B; c->factored = true; c->inverted = false; }
     return FAB_OK;
 }
@@ -226,7 +235,67 @@ int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2,
     if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
     if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    return launch_factor(c, theta, yerr2, B, ll, info, true);
+    int rc = launch_factor(c, theta, yerr2, B, ll, info, true);
+    if (rc != FAB_OK) return rc;
+    return FAB_OK;
+}
+
+// factorize + W = L^-1 + alpha, hyper-parameters copied into the context: models become resident.
+int fab_gp_fit_batch(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info) {
+    int rc = fab_gp_factorize_batch(c, theta, yerr2, B, ll, info);
+    if (rc != FAB_OK) return rc;
+    const GpData& gd = c->gd;
+    if ((rc = ensure(c, &c->dTheta, &c->capT, (size_t)B * gd.Pk)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->dYerr2, &c->capY, (size_t)B)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->dInfo, &c->capI, (size_t)B)) != FAB_OK) return rc;
+    FAB_CUDA(c, cudaMemcpyAsync(c->dTheta, theta, sizeof(double) * B * gd.Pk, cudaMemcpyDeviceToDevice, c->stream));
+    FAB_CUDA(c, cudaMemcpyAsync(c->dYerr2, yerr2, sizeof(double) * B, cudaMemcpyDeviceToDevice, c->stream));
+    FAB_CUDA(c, cudaMemcpyAsync(c->dInfo, info, sizeof(int) * B, cudaMemcpyDeviceToDevice, c->stream));
+    rc = launch_grad(c, c->dTheta, c->dYerr2, B, nullptr, c->dInfo);
+    if (rc != FAB_OK) return rc;
+    c->resident = true;
+    return FAB_OK;
+}
+
+static int launch_predict(fab_ctx* c, const double* T, int M, double* mu, double* var, double* cov,
+                          const double* dotvec, double* dot) {
+    const GpData& gd = c->gd;
+    PredictArgs a;
+    a.gd = gd; a.wk = c->wk; a.theta = c->dTheta; a.yerr2 = c->dYerr2; a.T = T; a.M = M;
+    a.mu = mu; a.var = var; a.cov = cov; a.dotvec = dotvec; a.dot = dot;
+    const bool want_cov = cov != nullptr;
+    if (want_cov && M > 64) return fail(c, FAB_EUNSUPPORTED, "full predictive covariance is limited to M <= 64 points");
+    const size_t s64 = predict_smem_bytes(64, gd.NT, gd.Np, gd.d, want_cov);
+    const size_t s32 = predict_smem_bytes(32, gd.NT, gd.Np, gd.d, false);
+    if (s64 <= (size_t)c->smem_optin) {
+        FAB_LAUNCH(gp_predict_kernel<64>, dim3((M + 63) / 64, c->wsB), NTHREADS, s64, c->stream, a);
+    } else if (!want_cov && s32 <= (size_t)c->smem_optin) {
+        FAB_LAUNCH(gp_predict_kernel<32>, dim3((M + 31) / 32, c->wsB), NTHREADS, s32, c->stream, a);
+    } else {
+        return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA prediction kernel");
+    }
+    FAB_CUDA(c, cudaGetLastError());
+    return FAB_OK;
+}
+
+int fab_gp_predict_batch(fab_ctx* c, const double* T, int M, double* mu, double* var, double* cov) {
+    if (!c) return FAB_EINVAL;
+    if (!c->resident) return fail(c, FAB_ESTATE, "fab_gp_fit_batch has not been called");
+    if (!T || M < 1 || (!mu && !var && !cov)) return fail(c, FAB_EINVAL, "bad argument");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    return launch_predict(c, T, M, mu, var, cov, nullptr, nullptr);
+}
+
+int fab_ei_batch(fab_ctx* c, const double* mu, const double* var, int B, int M, const double* y_max, double xi,
+                 double* ei, double* best_val, long long* best_idx) {
+    if (!c) return FAB_EINVAL;
+    if (!mu || !var || !y_max || B < 1 || M < 1) return fail(c, FAB_EINVAL, "bad argument");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    EiArgs a;
+    a.mu = mu; a.var = var; a.M = M; a.y_max = y_max; a.xi = xi; a.ei = ei; a.best_val = best_val; a.best_idx = best_idx;
+    FAB_LAUNCH(ei_argmax_kernel, B, NTHREADS, 0, c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    return FAB_OK;
 }
 
 int fab_gp_debug_get_factor(fab_ctx* c, int b, double* L_out) {

@@ -1,0 +1,272 @@
+// gp_predict.cuh -- kernel C: batched GP prediction for M candidates x B resident models.
+//
+// Replaces george's GP.predict (fabolas.py:187; entropy_search.py:130; acquisitions.py:31,103,109):
+//     mu* = K* alpha + mean ,   cov* = k(t,t) - K* K^-1 K*^T = k(t,t) - V^T V ,  V = W K*^T ,  W = L^-1
+// One CTA per (candidate block, model).  The cross-covariance panel K*^T (N x CB) is generated in
+// shared memory from the staged observations and candidates and never touches HBM; the W tiles of
+// the model stream from L2/HBM through a TMA bulk copy and feed DMMA tile products; variance,
+// the optional dot product with a per-model vector (used by the information-gain kernel:
+// cov(x, last representer) = k - vrl . V_x) and the optional full covariance of the block are
+// reduced straight from the accumulator fragments.
+#pragma once
+#include "gp_common.cuh"
+
+namespace fab {
+
+struct PredictArgs {
+    GpData gd;
+    GpWork wk;               // Lw holds W = L^-1 tiles, alpha
+    const double* theta;     // B x Pk (context copy made by factorize)
+    const double* yerr2;     // B
+    const double* T;         // M x D candidates (last column = basis input as given by the caller)
+    int M;
+    double* mu;              // B x M or null
+    double* var;             // B x M or null
+    double* cov;             // B x M x M or null (M <= 64 only)
+    const double* dotvec;    // B x Np or null
+    double* dot;             // B x M or null:  dot[b][c] = sum_obs V[obs][c] * dotvec[b][obs]
+};
+
+__host__ __device__ inline size_t predict_smem_bytes(int CB, int NT, int Np, int d, bool cov) {
+    size_t doubles = (size_t)NT * TS * CB + TILE_ELEMS + (cov ? TS * CB : 0) + (size_t)(d + 3) * Np + (size_t)(d + 1) * CB +
+                     3 * 8 * CB + 16;
+    return doubles * 8 + 64;
+}
+
+template <int CB>
+__global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(PredictArgs a) {
+    constexpr int MI = (CB == 64) ? 4 : 2;
+    constexpr int NJ = 2;
+    constexpr int NRG = (CB == 64) ? 2 : 4;        // warp row groups
+    FAB_DYN_SMEM(smem_raw);
+    const GpData& gd = a.gd;
+    const int b = blockIdx.y, blk = blockIdx.x;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int Np = gd.Np, NT = gd.NT, N = gd.N, d = gd.d, D = gd.D;
+    const bool want_cov = a.cov != nullptr;
+
+    double* Ks = reinterpret_cast<double*>(smem_raw);            // NT panels of 64 x CB
+    double* Wbuf = Ks + (size_t)NT * TS * CB;
+    double* Vscr = Wbuf + TILE_ELEMS;
+    double* zs = Vscr + (want_cov ? TS * CB : 0);
+    double* us = zs + (size_t)d * Np;
+    double* al = us + Np;
+    double* dv = al + Np;
+    double* tz = dv + Np;                                          // d x CB
+    double* tu = tz + (size_t)d * CB;                              // CB
+    double* part = tu + CB;                                        // 3 x 8 x CB
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(part + 3 * 8 * CB);
+
+    const Hyper h = decode_hyper(gd, a.theta + (size_t)b * gd.Pk, a.yerr2[b]);
+    const double* Lw = a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS;
+    const int c_base = blk * CB;
+
+    for (int e = tid; e < N * D; e += NTHREADS) {
+        const int i = e / D, k = e - i * D;
+        const double x = __ldg(&gd.X[e]);
+        if (k < d) zs[k * Np + i] = x * h.scale[k];
+        if (gd.family == 1 && k == d) us[i] = x;
+    }
+    for (int i = tid; i < Np; i += NTHREADS) {
+        if (i >= N) {
+            for (int k = 0; k < d; ++k) zs[k * Np + i] = 0.0;
+            us[i] = 0.0;
+        }
+        if (gd.family != 1 && i < N) us[i] = 0.0;
+        al[i] = a.wk.alpha[(size_t)b * Np + i];
+        dv[i] = a.dotvec ? a.dotvec[(size_t)b * Np + i] : 0.0;
+    }
+    for (int e = tid; e < CB * D; e += NTHREADS) {
+        const int c = e / D, k = e - c * D;
+        const int gc = c_base + c;
+        const double x = (gc < a.M) ? __ldg(&a.T[(size_t)gc * D + k]) : 0.0;
+        if (k < d) tz[k * CB + c] = x * h.scale[k];
+        if (k == d) tu[c] = x;
+    }
+    if (gd.family != 1) for (int c = tid; c < CB; c += NTHREADS) tu[c] = 0.0;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+
+    // ---- cross-covariance panel K*^T (obs x cand) + mean partials ----
+    double pmu[CB / 32];
+#pragma unroll
+    for (int q = 0; q < CB / 32; ++q) pmu[q] = 0.0;
+    for (int J = 0; J < NT; ++J) {
+        double* P = Ks + (size_t)J * TS * CB;
+#pragma unroll 1
+        for (int rr = 0; rr < 8; ++rr) {
+            const int r = 8 * w + rr, gi = TS * J + r;
+#pragma unroll
+            for (int q = 0; q < CB / 32; ++q) {
+                const int c = lane + 32 * q;
+                double v = 0.0;
+                if (gi < N && c_base + c < a.M) {
+                    double r2 = 0.0;
+                    for (int k = 0; k < d; ++k) {
+                        const double dz = zs[k * Np + gi] - tz[k * CB + c];
+                        r2 = fma(dz, dz, r2);
+                    }
+                    double m, gf;
+                    matern52(r2, m, gf);
+                    v = h.amp * m;
+                    if (gd.family == 1) v *= fma(us[gi] * tu[c], h.inv_g2, h.cb);
+                    pmu[q] = fma(v, al[gi], pmu[q]);
+                }
+                P[tixw<CB>(r, c)] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < CB / 32; ++q) part[w * CB + lane + 32 * q] = pmu[q];
+    __syncthreads();
+
+    // ---- V = W K*^T, reduced on the fly ----
+    const WarpTile wt = (CB == 64) ? warp_tile() : warp_tile_32();
+    double css[NJ][2], cdot[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) css[j][0] = css[j][1] = cdot[j][0] = cdot[j][1] = 0.0;
+    double cacc[4][2][2];
+    acc_zero(cacc);
+    unsigned phase = 0;
+    for (int I = 0; I < NT; ++I) {
+        double acc[MI][NJ][2];
+        acc_zero(acc);
+        for (int J = 0; J <= I; ++J) {
+            if (tid == 0) bulk_g2s(Wbuf, Lw + (size_t)tri_index(I, J) * TILE_ELEMS, TILE_BYTES, bar);
+            mbar_wait(bar, phase & 1u);
+            ++phase;
+            // W_II is lower triangular: columns k > m contribute nothing
+            tile_mma<false, false, false, MI, NJ, TS, CB>(acc, Wbuf, Ks + (size_t)J * TS * CB, wt, 0,
+                                                          (J == I) ? wt.m0 + 8 * MI : TS);
+            __syncthreads();               // everyone done with Wbuf before the next bulk copy lands
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const double dvr = dv[TS * I + wt.m0 + 8 * i + g];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    css[j][e] = fma(acc[i][j][e], acc[i][j][e], css[j][e]);
+                    cdot[j][e] = fma(acc[i][j][e], dvr, cdot[j][e]);
+                }
+        }
+        if (CB == 64 && want_cov) {
+            acc_store<MI, NJ, CB>(acc, Vscr, wt);
+            __syncthreads();
+            tile_mma<true, false, false, 4, 2, CB, CB>(cacc, Vscr, Vscr, warp_tile(), 0, TS);
+            __syncthreads();
+        }
+    }
+    // reduce the per-thread column partials over the 8 row lanes (g) of the warp
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                css[j][e] += __shfl_xor_sync(0xffffffffu, css[j][e], o);
+                cdot[j][e] += __shfl_xor_sync(0xffffffffu, cdot[j][e], o);
+            }
+        }
+    const int rg = (CB == 64) ? (w >> 2) : (w >> 1);
+    if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = wt.n0 + 8 * j + 2 * t + e;
+                part[(8 + rg) * CB + c] = css[j][e];
+                part[(16 + rg) * CB + c] = cdot[j][e];
+            }
+    }
+    __syncthreads();
+    if (tid < CB && c_base + tid < a.M) {
+        const int c = tid;
+        double m = 0.0, ss = 0.0, dd = 0.0;
+#pragma unroll
+        for (int q = 0; q < NWARPS; ++q) m += part[q * CB + c];
+#pragma unroll
+        for (int q = 0; q < NRG; ++q) { ss += part[(8 + q) * CB + c]; dd += part[(16 + q) * CB + c]; }
+        const size_t o = (size_t)b * a.M + c_base + c;
+        if (a.mu) a.mu[o] = m + gd.mean;
+        if (a.var) {
+            const double kss = h.amp * ((gd.family == 1) ? fma(tu[c] * tu[c], h.inv_g2, h.cb) : 1.0);
+            a.var[o] = kss - ss;
+        }
+        if (a.dot) a.dot[o] = dd;
+    }
+    if (CB == 64 && want_cov) {
+        const WarpTile wc = warp_tile();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c1 = wc.m0 + 8 * i + g, c2 = wc.n0 + 8 * j + 2 * t + e;
+                    if (c1 < a.M && c2 < a.M) {
+                        double r2 = 0.0;
+                        for (int k = 0; k < d; ++k) {
+                            const double dz = tz[k * CB + c1] - tz[k * CB + c2];
+                            r2 = fma(dz, dz, r2);
+                        }
+                        double m, gf;
+                        matern52(r2, m, gf);
+                        double v = h.amp * m;
+                        if (gd.family == 1) v *= fma(tu[c1] * tu[c2], h.inv_g2, h.cb);
+                        a.cov[((size_t)b * a.M + c1) * a.M + c2] = v - cacc[i][j][e];
+                    }
+                }
+    }
+}
+
+// EI (acquisitions.py:40-75) over B x M predictions + per-model argmax.  One CTA per model.
+//   sd = sqrt(var) ; u = (mu - y_max - xi) / sd ; ei = sd (u Phi(u) + phi(u)) ; 0 where sd <= 0
+struct EiArgs {
+    const double* mu; const double* var; int M;
+    const double* y_max;      // B
+    double xi;
+    double* ei;               // B x M or null
+    double* best_val;         // B or null
+    long long* best_idx;      // B or null
+};
+
+__device__ __forceinline__ double ei_value(double mu, double var, double y_max, double xi) {
+    const double sd = sqrt(var);
+    if (!(sd > 0.0)) return (sd <= 0.0) ? 0.0 : NAN;      // acquisitions.py:73 ; NaN variance stays NaN
+    const double u = (mu - y_max - xi) / sd;
+    const double cdf = 0.5 * erfc(-u * 0.70710678118654752440);
+    const double pdf = exp(-0.5 * u * u) * 0.39894228040143267794;
+    return sd * (u * cdf + pdf);
+}
+
+__global__ void __launch_bounds__(NTHREADS) ei_argmax_kernel(EiArgs a) {
+    __shared__ double sval[NWARPS];
+    __shared__ long long sidx[NWARPS];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const double ym = a.y_max[b];
+    double best = -INFINITY;
+    long long bi = -1;
+    for (long long c = tid; c < a.M; c += NTHREADS) {
+        const double v = ei_value(a.mu[(size_t)b * a.M + c], a.var[(size_t)b * a.M + c], ym, a.xi);
+        if (a.ei) a.ei[(size_t)b * a.M + c] = v;
+        if (v > best) { best = v; bi = c; }             // first maximum wins within a thread (ascending c)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { sval[w] = best; sidx[w] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 1; q < NWARPS; ++q)
+            if (sval[q] > best || (sval[q] == best && sidx[q] >= 0 && (bi < 0 || sidx[q] < bi))) { best = sval[q]; bi = sidx[q]; }
+        if (a.best_val) a.best_val[b] = best;
+        if (a.best_idx) a.best_idx[b] = bi;              // np.argmax: first occurrence of the maximum
+    }
+}
+
+}  // namespace fab

@@ -26,12 +26,18 @@ __device__ __forceinline__ int tix(int r, int c) { return r * TS + (c ^ ((r & 3)
 __host__ __device__ __forceinline__ int tri_index(int I, int J) { return I * (I + 1) / 2 + J; }
 
 // ---------------------------------------------------------------------------------------------
-// Accumulator fragment of one warp: 32 rows x 16 cols = 4 x 2 DMMA blocks.
-// acc[i][j][e] = C[m0 + 8i + g][n0 + 8j + 2t + e]
+// Accumulator fragment of one warp: (8*MI) rows x (8*NJ) cols = MI x NJ DMMA blocks.
+// acc[i][j][e] = C[m0 + 8i + g][n0 + 8j + 2t + e].  Default 4 x 2 (32 x 16): 8 warps tile 64 x 64.
+// LD* = row stride (doubles) of the swizzled operand; any multiple of 16 keeps the swizzle
+// conflict-free, so 64-wide tiles and 32-wide panels share the code.
 // ---------------------------------------------------------------------------------------------
+template <int LD>
+__device__ __forceinline__ int tixw(int r, int c) { return r * LD + (c ^ ((r & 3) << 2)); }
+
 struct WarpTile {
-    int m0, n0;   // origin of this warp's 32x16 block inside the 64x64 tile
+    int m0, n0;   // origin of this warp's block inside the output tile
 };
+// 8 warps as 2 x 4 blocks of 32 x 16 over a 64 x 64 output
 __device__ __forceinline__ WarpTile warp_tile() {
     const int w = threadIdx.x >> 5;
     WarpTile wt;
@@ -39,64 +45,74 @@ __device__ __forceinline__ WarpTile warp_tile() {
     wt.n0 = (w & 3) * 16;
     return wt;
 }
-
-__device__ __forceinline__ void acc_zero(double (&acc)[4][2][2]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+// 8 warps as 4 x 2 blocks of 16 x 16 over a 64 x 32 output
+__device__ __forceinline__ WarpTile warp_tile_32() {
+    const int w = threadIdx.x >> 5;
+    WarpTile wt;
+    wt.m0 = (w >> 1) * 16;
+    wt.n0 = (w & 1) * 16;
+    return wt;
 }
-__device__ __forceinline__ void acc_load(double (&acc)[4][2][2], const double* C, WarpTile wt) {
+
+template <int MI, int NJ>
+__device__ __forceinline__ void acc_zero(double (&acc)[MI][NJ][2]) {
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+template <int MI, int NJ, int LD = TS>
+__device__ __forceinline__ void acc_load(double (&acc)[MI][NJ][2], const double* C, WarpTile wt) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const double2 v = *reinterpret_cast<const double2*>(&C[tix(wt.m0 + 8 * i + g, wt.n0 + 8 * j + 2 * t)]);
+        for (int j = 0; j < NJ; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(&C[tixw<LD>(wt.m0 + 8 * i + g, wt.n0 + 8 * j + 2 * t)]);
             acc[i][j][0] = v.x; acc[i][j][1] = v.y;
         }
 }
-__device__ __forceinline__ void acc_store(const double (&acc)[4][2][2], double* C, WarpTile wt) {
+template <int MI, int NJ, int LD = TS>
+__device__ __forceinline__ void acc_store(const double (&acc)[MI][NJ][2], double* C, WarpTile wt) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             double2 v; v.x = acc[i][j][0]; v.y = acc[i][j][1];
-            *reinterpret_cast<double2*>(&C[tix(wt.m0 + 8 * i + g, wt.n0 + 8 * j + 2 * t)]) = v;
+            *reinterpret_cast<double2*>(&C[tixw<LD>(wt.m0 + 8 * i + g, wt.n0 + 8 * j + 2 * t)]) = v;
         }
 }
 
 // acc += sign * opA(A) * opB(B) restricted to k in [k_lo, k_hi) (multiples of 4).
 //   opA(A)[m][k] = TA ? A[k][m] : A[m][k]        opB(B)[k][n] = TB ? B[n][k] : B[k][n]
-template <bool TA, bool TB, bool NEG>
-__device__ __forceinline__ void tile_mma(double (&acc)[4][2][2], const double* __restrict__ A,
+template <bool TA, bool TB, bool NEG, int MI = 4, int NJ = 2, int LDA = TS, int LDB = TS>
+__device__ __forceinline__ void tile_mma(double (&acc)[MI][NJ][2], const double* __restrict__ A,
                                          const double* __restrict__ B, WarpTile wt, int k_lo, int k_hi) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    // row-fragment addressing: (row, k0 + t) -> row*64 + ((k0 ^ sg) | t),  sg = (g & 3) << 2
-    // col-fragment addressing: (k0 + t, col) -> (k0 + t)*64 + (col ^ (t << 2))
+    // row-fragment addressing: (row, k0 + t) -> row*LD + ((k0 ^ sg) | t),  sg = (g & 3) << 2
+    // col-fragment addressing: (k0 + t, col) -> (k0 + t)*LD + (col ^ (t << 2))
     const int sg = (g & 3) << 2, st = t << 2;
-    int a_off[4], b_off[2];
+    int a_off[MI], b_off[NJ];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a_off[i] = TA ? (t * TS + ((wt.m0 + 8 * i + g) ^ st)) : ((wt.m0 + 8 * i + g) * TS + t);
+    for (int i = 0; i < MI; ++i) a_off[i] = TA ? (t * LDA + ((wt.m0 + 8 * i + g) ^ st)) : ((wt.m0 + 8 * i + g) * LDA + t);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) b_off[j] = TB ? ((wt.n0 + 8 * j + g) * TS + t) : (t * TS + ((wt.n0 + 8 * j + g) ^ st));
+    for (int j = 0; j < NJ; ++j) b_off[j] = TB ? ((wt.n0 + 8 * j + g) * LDB + t) : (t * LDB + ((wt.n0 + 8 * j + g) ^ st));
 #pragma unroll 4
     for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
         const int krow = k0 ^ sg;      // swizzled column base for row fragments
-        const int kcol = k0 * TS;      // row base for column fragments
-        double a[4], b[2];
+        double a[MI], b[NJ];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double v = A[a_off[i] + (TA ? kcol : krow)];
+        for (int i = 0; i < MI; ++i) {
+            const double v = A[a_off[i] + (TA ? k0 * LDA : krow)];
             a[i] = NEG ? -v : v;
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) b[j] = B[b_off[j] + (TB ? krow : kcol)];
+        for (int j = 0; j < NJ; ++j) b[j] = B[b_off[j] + (TB ? krow : k0 * LDB)];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 

@@ -72,11 +72,26 @@ int fab_gp_set_data(fab_ctx* ctx, int family, const double* X, int N, int D, con
 int fab_gp_loglik_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll,
                         double* grad, int* info);
 
-/* Factorise B models and keep them resident in the context for prediction / acquisition calls:
- * replaces the per-hyper-sample model construction `GP(kernel, mean); regressor.compute(x, yerr)`
- * (fabolas.py:171-176, 245-248; entropy_search.py:118-119).  Also returns ll/info like loglik.   */
+/* Cholesky factors of B models into the context workspace (tiled, swizzled; test / debug use).  */
 int fab_gp_factorize_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll,
                            int* info);
+
+/* Fit B models and keep them RESIDENT for prediction / acquisition calls: factorise, invert the
+ * factor (W = L^-1), alpha = K^-1 (y - mean), copy the hyper-parameters.  Replaces the
+ * per-hyper-sample `GP(kernel, mean); regressor.compute(x, yerr)` of fabolas.py:171-176, 245-248 and
+ * entropy_search.py:118-119.  Also returns ll / info like fab_gp_loglik_batch.                    */
+int fab_gp_fit_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll, int* info);
+
+/* GP.predict for every resident model (fabolas.py:187; entropy_search.py:130; acquisitions.py:31,
+ * 103,109): T is M x D row-major.  mu, var: B x M (latent mean / variance, no noise term) or NULL;
+ * cov: B x M x M or NULL (full predictive covariance, M <= 64: the reference uses M in {1,50,51}). */
+int fab_gp_predict_batch(fab_ctx* ctx, const double* T, int M, double* mu, double* var, double* cov);
+
+/* acquisitions.expected_improvement (acquisitions.py:40-75) on B x M predictive moments, plus the
+ * np.argmax of expected_improvement.get_candidate (expected_improvement.py:92-93) per model:
+ * ei (B x M), best_val (B), best_idx (B, int64) may each be NULL.  y_max: B incumbents.           */
+int fab_ei_batch(fab_ctx* ctx, const double* mu, const double* var, int B, int M, const double* y_max,
+                 double xi, double* ei, double* best_val, long long* best_idx);
 
 /* Debug / test access: copy the dense lower Cholesky factor of walker b (N x N row-major, device)
  * out of the tiled workspace left by the last fab_gp_loglik_batch(grad != NULL) / factorize call. */
