@@ -38,7 +38,10 @@ SIGNATURES = {
     "fab_gp_loglik_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
     "fab_gp_factorize_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
     "fab_gp_fit_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
-    "fab_gp_predict_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp]),
+    "fab_gp_predict_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp]),
+    "fab_epmgp_joint_min_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fab_es_setup": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int]),
+    "fab_es_information_gain_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
 }
@@ -196,13 +199,14 @@ class Engine:
         T = self.tensor(T)
         if T.dim() == 1:
             T = T[None]
-        if T.shape[1] != self.D:
-            raise ValueError(f"T must have {self.D} columns")
-        M = T.shape[0]
+        per_model = T.dim() == 3          # (B, M, D): every model predicts at its own points
+        if T.shape[-1] != self.D or (per_model and T.shape[0] != self.B):
+            raise ValueError(f"T must be (M, {self.D}) or ({self.B}, M, {self.D})")
+        M = T.shape[-2]
         mu = self.empty(self.B, M)
         var = self.empty(self.B, M) if want_var else None
         cov = self.empty(self.B, M, M) if want_cov else None
-        self._check(self.lib.fab_gp_predict_batch(self._ctx, _ptr(T), M, _ptr(mu), _ptr(var), _ptr(cov)),
+        self._check(self.lib.fab_gp_predict_batch(self._ctx, _ptr(T), int(per_model), M, _ptr(mu), _ptr(var), _ptr(cov)),
                     "fab_gp_predict_batch")
         out = [mu]
         if want_var:
@@ -226,6 +230,51 @@ class Engine:
         self._check(self.lib.fab_ei_batch(self._ctx, _ptr(mu), _ptr(var), B, M, _ptr(y_max), float(xi), _ptr(ei),
                                           _ptr(bv), _ptr(bi)), "fab_ei_batch")
         return ei, bv, bi
+
+    def joint_min(self, mu, Sigma, with_derivatives: bool = True, return_sweeps: bool = False):
+        """Batched epmgp.joint_min: mu (B, Z), Sigma (B, Z, Z) -> logP [, dMu, dSigma, dMuMu], info."""
+        mu, Sigma = self.tensor(mu), self.tensor(Sigma)
+        if mu.dim() == 1:
+            mu, Sigma = mu[None], Sigma[None]
+        B, Z = mu.shape
+        T = Z * (Z + 1) // 2
+        logP = self.empty(B, Z)
+        info = self.empty(B, dtype=torch.int32)
+        sweeps = self.empty(B, Z, dtype=torch.int32) if return_sweeps else None
+        dMu = self.empty(B, Z, Z) if with_derivatives else None
+        dSg = self.empty(B, Z, T) if with_derivatives else None
+        dMM = self.empty(B, Z, Z, Z) if with_derivatives else None
+        self._check(self.lib.fab_epmgp_joint_min_batch(self._ctx, _ptr(mu), _ptr(Sigma), B, Z, _ptr(logP), _ptr(dMu),
+                                                       _ptr(dSg), _ptr(dMM), _ptr(info), _ptr(sweeps)),
+                    "fab_epmgp_joint_min_batch")
+        out = (logP, dMu, dSg, dMM, info) if with_derivatives else (logP, info)
+        return out + (sweeps,) if return_sweeps else out
+
+    def es_setup(self, reps, cov_reps, p_min, U, Omega):
+        """Entropy-Search state of the resident models.  reps (B, Z, D); cov_reps (B, Z, Z) unclipped;
+        p_min = (logP, dMu, dSigma, dMuMu) batched; U (B, Z); Omega (B, I, Z)."""
+        reps, cov_reps, U, Omega = (self.tensor(t) for t in (reps, cov_reps, U, Omega))
+        logP, dMu, dSg, dMM = (self.tensor(t) for t in p_min[:4])
+        B, Z, D = reps.shape
+        if B != self.B or D != self.D or Omega.shape[0] != B or Omega.shape[2] != Z:
+            raise ValueError("shape mismatch in es_setup")
+        self._es_keep = (reps, cov_reps, U, Omega, logP, dMu, dSg, dMM)     # alive until the stream has consumed them
+        self._check(self.lib.fab_es_setup(self._ctx, _ptr(reps), Z, _ptr(cov_reps), _ptr(logP), _ptr(dMu), _ptr(dSg),
+                                          _ptr(dMM), _ptr(U), _ptr(Omega), Omega.shape[1]), "fab_es_setup")
+
+    def information_gain(self, Xc, return_mixture: bool = False):
+        """Information gain of every row of Xc (M, D) -> ig (M,), nan_flag (M,) [, mix_mean, mix_var]."""
+        Xc = self.tensor(Xc)
+        if Xc.dim() == 1:
+            Xc = Xc[None]
+        M = Xc.shape[0]
+        ig = self.empty(M)
+        flag = self.empty(M, dtype=torch.int32)
+        mm = self.empty(M) if return_mixture else None
+        mv = self.empty(M) if return_mixture else None
+        self._check(self.lib.fab_es_information_gain_batch(self._ctx, _ptr(Xc), M, _ptr(ig), _ptr(flag), _ptr(mm), _ptr(mv)),
+                    "fab_es_information_gain_batch")
+        return (ig, flag, mm, mv) if return_mixture else (ig, flag)
 
     def debug_factor(self, b: int) -> torch.Tensor:
         L = self.empty(self.N, self.N)

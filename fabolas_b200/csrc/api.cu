@@ -3,6 +3,8 @@
 #include "gp_factor.cuh"
 #include "gp_grad.cuh"
 #include "gp_predict.cuh"
+#include "epmgp.cuh"
+#include "ig.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -27,6 +29,13 @@ struct fab_ctx {
     double* dYerr2 = nullptr; size_t capY = 0;
     int* dInfo = nullptr; size_t capI = 0;
     bool resident = false;  // factorize_batch completed: W, alpha, theta resident
+    // Entropy-Search state (fab_es_setup) and scratch for information-gain sweeps
+    EsState es{};
+    bool es_ready = false;
+    size_t cap_es[7] = {0, 0, 0, 0, 0, 0, 0};
+    double* sc_mu = nullptr; double* sc_var = nullptr; double* sc_dot = nullptr; double* sc_c0 = nullptr;
+    double* sc_part = nullptr; double* sc_vmix = nullptr; double* sc_mmix = nullptr;
+    size_t cap_sc[7] = {0, 0, 0, 0, 0, 0, 0};
     int wsB = 0;            // walkers the factor workspace currently describes
     bool factored = false;
     bool inverted = false;  // workspace holds W = L^-1 (and alpha) instead of L
@@ -100,6 +109,9 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
     cudaFuncSetAttribute(gp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(gp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(gp_predict_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(epmgp_ep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(epmgp_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(es_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(gp_predict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
 #endif
     *out = c;
@@ -110,6 +122,10 @@ int fab_ctx_destroy(fab_ctx* c) {
     if (!c) return FAB_EINVAL;
     cudaSetDevice(c->device);
     cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dTheta); cudaFree(c->dYerr2); cudaFree(c->dInfo);
+    cudaFree(c->es.rl); cudaFree(c->es.vrl); cudaFree(c->es.coef); cudaFree(c->es.logP); cudaFree(c->es.logU);
+    cudaFree(c->es.base); cudaFree(c->es.omega);
+    cudaFree(c->sc_mu); cudaFree(c->sc_var); cudaFree(c->sc_dot); cudaFree(c->sc_c0); cudaFree(c->sc_part);
+    cudaFree(c->sc_vmix); cudaFree(c->sc_mmix);
 #ifndef FAB_CUSIM
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 #endif
@@ -197,6 +213,7 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
     c->resident = false;
+    c->es_ready = false;
     if (need_ws) { c->wsB = B; c->factored = true; c->inverted = false; }
     return FAB_OK;
 }
@@ -257,12 +274,12 @@ int fab_gp_fit_batch(fab_ctx* c, const double* theta, const double* yerr2, int B
     return FAB_OK;
 }
 
-static int launch_predict(fab_ctx* c, const double* T, int M, double* mu, double* var, double* cov,
-                          const double* dotvec, double* dot) {
+static int launch_predict(fab_ctx* c, const double* T, long long T_bstride, int M, double* mu, double* var,
+                          double* cov, const double* dotvec, double* dot, double* vcol = nullptr, int vcol_index = 0) {
     const GpData& gd = c->gd;
     PredictArgs a;
-    a.gd = gd; a.wk = c->wk; a.theta = c->dTheta; a.yerr2 = c->dYerr2; a.T = T; a.M = M;
-    a.mu = mu; a.var = var; a.cov = cov; a.dotvec = dotvec; a.dot = dot;
+    a.gd = gd; a.wk = c->wk; a.theta = c->dTheta; a.yerr2 = c->dYerr2; a.T = T; a.T_bstride = T_bstride; a.M = M;
+    a.mu = mu; a.var = var; a.cov = cov; a.dotvec = dotvec; a.dot = dot; a.vcol = vcol; a.vcol_index = vcol_index;
     const bool want_cov = cov != nullptr;
     if (want_cov && M > 64) return fail(c, FAB_EUNSUPPORTED, "full predictive covariance is limited to M <= 64 points");
     const size_t s64 = predict_smem_bytes(64, gd.NT, gd.Np, gd.d, want_cov);
@@ -278,12 +295,107 @@ static int launch_predict(fab_ctx* c, const double* T, int M, double* mu, double
     return FAB_OK;
 }
 
-int fab_gp_predict_batch(fab_ctx* c, const double* T, int M, double* mu, double* var, double* cov) {
+int fab_gp_predict_batch(fab_ctx* c, const double* T, int per_model, int M, double* mu, double* var, double* cov) {
     if (!c) return FAB_EINVAL;
     if (!c->resident) return fail(c, FAB_ESTATE, "fab_gp_fit_batch has not been called");
     if (!T || M < 1 || (!mu && !var && !cov)) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    return launch_predict(c, T, M, mu, var, cov, nullptr, nullptr);
+    return launch_predict(c, T, per_model ? (long long)M * c->gd.D : 0, M, mu, var, cov, nullptr, nullptr);
+}
+
+int fab_epmgp_joint_min_batch(fab_ctx* c, const double* mu, const double* Sigma, int B, int Z, double* logP,
+                              double* dMu, double* dSigma, double* dMuMu, int* info, int* sweeps) {
+    if (!c) return FAB_EINVAL;
+    if (!mu || !Sigma || !logP || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
+    if (Z < 1 || Z > EP_MAXZ) return fail(c, FAB_EUNSUPPORTED, "EPMGP supports 1 <= Z <= 64 representer points");
+    const int wd = (dMu && dSigma && dMuMu) ? 1 : 0;
+    if (!wd && (dMu || dSigma || dMuMu)) return fail(c, FAB_EINVAL, "pass all three derivative buffers or none");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    FAB_CUDA(c, cudaMemsetAsync(info, 0, sizeof(int) * B, c->stream));
+    EpArgs a;
+    a.mu = mu; a.Sigma = Sigma; a.Z = Z; a.logP = logP; a.dMu = dMu; a.dSigma = dSigma; a.dMuMu = dMuMu;
+    a.info = info; a.sweeps = sweeps; a.with_derivatives = wd;
+    FAB_LAUNCH(epmgp_ep_kernel, dim3(Z, B), EP_THREADS, ep_smem_bytes(Z), c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    FAB_LAUNCH(epmgp_normalize_kernel, B, 256, ep_norm_smem_bytes(Z), c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    return FAB_OK;
+}
+
+namespace {
+__global__ void gather_last_rep_kernel(const double* reps, int Z, int D, double* rl) {
+    const int b = blockIdx.x;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) rl[(size_t)b * D + k] = reps[((size_t)b * Z + (Z - 1)) * D + k];
+}
+}  // namespace
+
+int fab_es_setup(fab_ctx* c, const double* reps, int Z, const double* cov_reps, const double* logP, const double* dMu,
+                 const double* dSigma, const double* dMuMu, const double* U, const double* Omega, int I) {
+    if (!c) return FAB_EINVAL;
+    if (!c->resident) return fail(c, FAB_ESTATE, "fab_gp_fit_batch has not been called");
+    if (!reps || !cov_reps || !logP || !dMu || !dSigma || !dMuMu || !U || !Omega) return fail(c, FAB_EINVAL, "null pointer");
+    if (Z < 1 || Z > EP_MAXZ || I < 1) return fail(c, FAB_EUNSUPPORTED, "need 1 <= Z <= 64 representers and I >= 1 innovations");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    const GpData& gd = c->gd;
+    const int B = c->wsB;
+    EsState& st = c->es;
+    int rc;
+    if ((rc = ensure(c, &st.rl, &c->cap_es[0], (size_t)B * gd.D)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &st.vrl, &c->cap_es[1], (size_t)B * gd.Np)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &st.coef, &c->cap_es[2], (size_t)B * 8 * Z)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &st.logP, &c->cap_es[3], (size_t)B * Z)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &st.logU, &c->cap_es[4], (size_t)B * Z)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &st.base, &c->cap_es[5], (size_t)B)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &st.omega, &c->cap_es[6], (size_t)B * I * Z)) != FAB_OK) return rc;
+    st.Z = Z; st.I = I;
+    FAB_CUDA(c, cudaMemcpyAsync(st.omega, Omega, sizeof(double) * B * I * Z, cudaMemcpyDeviceToDevice, c->stream));
+    FAB_LAUNCH(gather_last_rep_kernel, B, 32, 0, c->stream, reps, Z, gd.D, st.rl);
+    FAB_CUDA(c, cudaGetLastError());
+    // vrl_b = W_b k_b(X, rep_last_b): one-point per-model prediction, keeping column 0 of V
+    FAB_CUDA(c, cudaMemsetAsync(st.vrl, 0, sizeof(double) * B * gd.Np, c->stream));
+    rc = launch_predict(c, st.rl, gd.D, 1, nullptr, nullptr, nullptr, nullptr, nullptr, st.vrl, 0);
+    if (rc != FAB_OK) return rc;
+    EsSetupArgs a;
+    a.st = st; a.cov_reps = cov_reps; a.logP = logP; a.dMu = dMu; a.dSigma = dSigma; a.dMuMu = dMuMu; a.U = U;
+    FAB_LAUNCH(es_setup_kernel, B, ES_THREADS, 0, c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    c->es_ready = true;
+    return FAB_OK;
+}
+
+int fab_es_information_gain_batch(fab_ctx* c, const double* Xc, int M, double* ig, int* nan_flag, double* mix_mean,
+                                  double* mix_var) {
+    if (!c) return FAB_EINVAL;
+    if (!c->es_ready) return fail(c, FAB_ESTATE, "fab_es_setup has not been called");
+    if (!Xc || !ig || M < 1) return fail(c, FAB_EINVAL, "bad argument");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    const GpData& gd = c->gd;
+    const int B = c->wsB;
+    int rc;
+    if ((rc = ensure(c, &c->sc_mu, &c->cap_sc[0], (size_t)B * M)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->sc_var, &c->cap_sc[1], (size_t)B * M)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->sc_dot, &c->cap_sc[2], (size_t)B * M)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->sc_c0, &c->cap_sc[3], (size_t)B * M)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->sc_part, &c->cap_sc[4], (size_t)B * M)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->sc_vmix, &c->cap_sc[5], (size_t)M)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->sc_mmix, &c->cap_sc[6], (size_t)M)) != FAB_OK) return rc;
+    rc = launch_predict(c, Xc, 0, M, c->sc_mu, c->sc_var, nullptr, c->es.vrl, c->sc_dot);
+    if (rc != FAB_OK) return rc;
+    EsMixArgs m;
+    m.gd = gd; m.theta = c->dTheta; m.yerr2 = c->dYerr2; m.st = c->es; m.Xc = Xc; m.M = M; m.B = B;
+    m.mu = c->sc_mu; m.var = c->sc_var; m.dot = c->sc_dot; m.vmix = c->sc_vmix; m.mmix = c->sc_mmix; m.c0 = c->sc_c0;
+    FAB_LAUNCH(es_mix_kernel, M, ES_THREADS, 0, c->stream, m);
+    FAB_CUDA(c, cudaGetLastError());
+    EsEntropyArgs e;
+    e.st = c->es; e.M = M; e.B = B; e.vmix = c->sc_vmix; e.c0 = c->sc_c0; e.partial = c->sc_part;
+    FAB_LAUNCH(es_entropy_kernel, dim3((M + ES_XPB - 1) / ES_XPB, B), ES_THREADS,
+               es_entropy_smem_bytes(c->es.Z, c->es.I), c->stream, e);
+    FAB_CUDA(c, cudaGetLastError());
+    FAB_LAUNCH(es_reduce_kernel, (M + 127) / 128, 128, 0, c->stream, c->sc_part, M, B, ig, nan_flag);
+    FAB_CUDA(c, cudaGetLastError());
+    if (mix_mean) FAB_CUDA(c, cudaMemcpyAsync(mix_mean, c->sc_mmix, sizeof(double) * M, cudaMemcpyDeviceToDevice, c->stream));
+    if (mix_var) FAB_CUDA(c, cudaMemcpyAsync(mix_var, c->sc_vmix, sizeof(double) * M, cudaMemcpyDeviceToDevice, c->stream));
+    return FAB_OK;
 }
 
 int fab_ei_batch(fab_ctx* c, const double* mu, const double* var, int B, int M, const double* y_max, double xi,

@@ -19,12 +19,15 @@ struct PredictArgs {
     const double* theta;     // B x Pk (context copy made by factorize)
     const double* yerr2;     // B
     const double* T;         // M x D candidates (last column = basis input as given by the caller)
+    long long T_bstride;     // 0: all models share T ; M*D: model b reads T + b*T_bstride (per-model points)
     int M;
     double* mu;              // B x M or null
     double* var;             // B x M or null
     double* cov;             // B x M x M or null (M <= 64 only)
     const double* dotvec;    // B x Np or null
     double* dot;             // B x M or null:  dot[b][c] = sum_obs V[obs][c] * dotvec[b][obs]
+    double* vcol;            // B x Np or null: column `vcol_index` of V = W K*^T (first block only)
+    int vcol_index;
 };
 
 __host__ __device__ inline size_t predict_smem_bytes(int CB, int NT, int Np, int d, bool cov) {
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(PredictArgs a) 
     for (int e = tid; e < CB * D; e += NTHREADS) {
         const int c = e / D, k = e - c * D;
         const int gc = c_base + c;
-        const double x = (gc < a.M) ? __ldg(&a.T[(size_t)gc * D + k]) : 0.0;
+        const double x = (gc < a.M) ? __ldg(&a.T[(size_t)b * a.T_bstride + (size_t)gc * D + k]) : 0.0;
         if (k < d) tz[k * CB + c] = x * h.scale[k];
         if (k == d) tu[c] = x;
     }
@@ -150,6 +153,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(PredictArgs a) 
                     css[j][e] = fma(acc[i][j][e], acc[i][j][e], css[j][e]);
                     cdot[j][e] = fma(acc[i][j][e], dvr, cdot[j][e]);
                 }
+        }
+        if (a.vcol && blk == 0) {
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (wt.n0 + 8 * j + 2 * t + e == a.vcol_index)
+                            a.vcol[(size_t)b * Np + TS * I + wt.m0 + 8 * i + g] = acc[i][j][e];
         }
         if (CB == 64 && want_cov) {
             acc_store<MI, NJ, CB>(acc, Vscr, wt);

@@ -83,15 +83,46 @@ int fab_gp_factorize_batch(fab_ctx* ctx, const double* theta, const double* yerr
 int fab_gp_fit_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll, int* info);
 
 /* GP.predict for every resident model (fabolas.py:187; entropy_search.py:130; acquisitions.py:31,
- * 103,109): T is M x D row-major.  mu, var: B x M (latent mean / variance, no noise term) or NULL;
+ * 103,109): T is M x D row-major, shared by all models (per_model = 0) or B x M x D with each model
+ * predicting at its own points (per_model = 1: the per-hyper-sample representer points of
+ * fabolas.py:180-188).  mu, var: B x M (latent mean / variance, no noise term) or NULL;
  * cov: B x M x M or NULL (full predictive covariance, M <= 64: the reference uses M in {1,50,51}). */
-int fab_gp_predict_batch(fab_ctx* ctx, const double* T, int M, double* mu, double* var, double* cov);
+int fab_gp_predict_batch(fab_ctx* ctx, const double* T, int per_model, int M, double* mu, double* var,
+                         double* cov);
 
 /* acquisitions.expected_improvement (acquisitions.py:40-75) on B x M predictive moments, plus the
  * np.argmax of expected_improvement.get_candidate (expected_improvement.py:92-93) per model:
  * ei (B x M), best_val (B), best_idx (B, int64) may each be NULL.  y_max: B incumbents.           */
 int fab_ei_batch(fab_ctx* ctx, const double* mu, const double* var, int B, int M, const double* y_max,
                  double xi, double* ei, double* best_val, long long* best_idx);
+
+/* epmgp.joint_min(mu, Sigma, with_derivatives) for B (mu, Sigma) pairs at once (epmgp.py:52-129;
+ * call sites fabolas.py:209, entropy_search.py:141):  mu B x Z, Sigma B x Z x Z  ->
+ *   logP B x Z ; dMu B x Z x Z ; dSigma B x Z x Z(Z+1)/2 (row-major lower order) ; dMuMu B x Z x Z x Z
+ * (pass all three derivative buffers, or NULL for with_derivatives=False).  Z <= 64.
+ *   info B : 0 ok; 1 = EP produced a NaN variance (the reference raises Exception, epmgp.py:250-253);
+ *            2 = Cholesky of I + R^T Sigma R failed after the jitter ladder (reference raises LinAlgError).
+ *   sweeps B x Z or NULL: EP sweeps used per "k is the minimum" problem (diagnostic).             */
+int fab_epmgp_joint_min_batch(fab_ctx* ctx, const double* mu, const double* Sigma, int B, int Z,
+                              double* logP, double* dMu, double* dSigma, double* dMuMu, int* info,
+                              int* sweeps);
+
+/* Entropy-Search state for the resident models (the per-hyper-sample lists built by
+ * fabolas.get_candidate, fabolas.py:149-221, and entropy_search.entropy_search, entropy_search.py:
+ * 108-153): representer points reps (B x Z x D), their UNCLIPPED posterior covariance cov_reps
+ * (B x Z x Z, what compute_innovations re-predicts, acquisitions.py:31), p_min = joint_min outputs
+ * (logP, dMu, dSigma, dMuMu), U (B x Z, EI at the representers) and Omega (B x I x Z innovation
+ * vectors).  Everything the information gain needs is reduced to O(B Z) coefficients inside the
+ * context; the caller's buffers are not referenced after the call returns (stream order).         */
+int fab_es_setup(fab_ctx* ctx, const double* reps, int Z, const double* cov_reps, const double* logP,
+                 const double* dMu, const double* dSigma, const double* dMuMu, const double* U,
+                 const double* Omega, int I);
+
+/* acquisitions.information_gain (acquisitions.py:119-167) for M test points at once: ig (M),
+ * nan_flag (M or NULL; 1 where the reference raises ArithmeticError), and optionally the mixture
+ * predictive mean / variance of predict_testpoint_george (acquisitions.py:99-116), M each.        */
+int fab_es_information_gain_batch(fab_ctx* ctx, const double* Xc, int M, double* ig, int* nan_flag,
+                                  double* mix_mean, double* mix_var);
 
 /* Debug / test access: copy the dense lower Cholesky factor of walker b (N x N row-major, device)
  * out of the tiled workspace left by the last fab_gp_loglik_batch(grad != NULL) / factorize call. */

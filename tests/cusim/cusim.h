@@ -265,3 +265,16 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+// block-wide OR (CUDA's __syncthreads_or): two rendezvous points around a shared accumulator
+static inline int __syncthreads_or(int pred) {
+    static int acc_[2] = {0, 0};
+    static unsigned long long gen_ = 0;
+    const unsigned long long my = gen_;
+    if (pred) acc_[my & 1] = 1;
+    cusim::block_barrier();
+    if (gen_ == my) { gen_ = my + 1; acc_[(my + 1) & 1] = 0; }
+    const int r = acc_[my & 1];
+    cusim::block_barrier();
+    CUSIM_RESTORE_TID();
+    return r;
+}

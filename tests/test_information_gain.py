@@ -1,0 +1,93 @@
+"""Entropy-Search information gain: CUDA path vs the REFERENCE's own acquisitions.information_gain
+(golden acq_ref.npz, produced by /root/reference/acquisitions.py + epmgp.py) and vs the numpy oracle."""
+import numpy as np
+import pytest
+
+from oracle import acq_oracle as ao
+from oracle import epmgp_oracle as eo
+from oracle import george_oracle as go
+from tests.conftest import golden
+
+TOL = 1e-8      # relative, on information-gain values of O(1..10)
+
+
+def _golden_setup(eng):
+    g = golden("acq_ref.npz")
+    D = g["Xtrain"].shape[1]
+    eng.set_data(1, g["Xtrain"], g["y"], float(g["y"].mean()), D)
+    eng.fit(g["theta"], g["yerr2"])
+    mu, var, cov = eng.predict(g["reps"], want_cov=True)            # per-model representer points
+    p_min = (g["pmin_logP"], g["pmin_dMu"], g["pmin_dSg"], g["pmin_dMM"])
+    eng.es_setup(g["reps"], cov, p_min, g["U"], g["Omega"])
+    return g
+
+
+def test_information_gain_matches_reference_emulated(sim_engine):
+    g = _golden_setup(sim_engine)
+    ig, flag, mm, mv = sim_engine.information_gain(g["tests"], return_mixture=True)
+    assert int(flag.numpy().max()) == 0
+    assert np.max(np.abs(ig.numpy() - g["ig"]) / np.abs(g["ig"])) < TOL
+    assert np.allclose(mm.numpy(), g["pred_model"][:, 0], rtol=1e-10, atol=1e-12)
+    assert np.allclose(mv.numpy(), g["pred_model"][:, 1], rtol=1e-9, atol=1e-12)
+    one, _ = sim_engine.information_gain(g["tests"][2])
+    assert abs(float(one[0]) - g["ig"][2]) < TOL * abs(g["ig"][2])
+
+
+@pytest.mark.gpu
+def test_information_gain_matches_reference_gpu(gpu_engine):
+    g = _golden_setup(gpu_engine)
+    ig, flag, mm, mv = gpu_engine.information_gain(g["tests"], return_mixture=True)
+    assert int(flag.cpu().numpy().max()) == 0
+    assert np.max(np.abs(ig.cpu().numpy() - g["ig"]) / np.abs(g["ig"])) < TOL
+    assert np.allclose(mv.cpu().numpy(), g["pred_model"][:, 1], rtol=1e-9, atol=1e-12)
+    # information_gain_cost (acquisitions.py:170-183): cost models are a second resident problem
+    from fabolas_b200 import Engine
+    cost = Engine("cuda:0")
+    cost.set_data(1, g["Xraw"], g["c"], float(g["c"].mean()), g["Xraw"].shape[1])
+    cost.fit(g["ctheta"], g["yerr2"])
+    cmu, = cost.predict(g["tests"], want_var=False)
+    igc = ig.cpu().numpy() / (cmu.cpu().numpy().mean(0) + 1e-4)
+    assert np.max(np.abs(igc - g["igc"]) / np.abs(g["igc"])) < TOL
+    cost.close()
+
+
+@pytest.mark.gpu
+def test_information_gain_full_pipeline_vs_oracle_gpu(gpu_engine):
+    """Config-3 shape at reduced batch: N=256, Z=50 representers, I=20 innovations, whole setup
+    (predict at representers -> EI -> EPMGP -> IG) on the GPU, oracle for a few candidates."""
+    from fabolas_b200.workloads import gp_workload
+    import torch
+    B, Z, I, M = 4, 50, 20, 40
+    w = gp_workload(2, n_walkers=B)
+    rng = np.random.default_rng(3)
+    lo = np.array([4, 4, 4, 32, -6, 1 / 256]); hi = np.array([9, 9, 9, 512, -1, 1.0])
+    reps = rng.uniform(lo, hi, (B, Z, 6))
+    Omega = rng.standard_normal((B, I, Z))
+    cand = rng.uniform(lo, hi, (M, 6))
+    eng = gpu_engine
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+    eng.fit(w["theta"], w["yerr2"])
+    mu, var, cov = eng.predict(reps, want_cov=True)
+    eps = np.finfo(float).eps
+    cov_clip = torch.clamp(cov, min=eps)                                           # fabolas.py:192
+    ymax = mu.max(dim=1).values + 0.1
+    ei, _, _ = eng.expected_improvement(mu, torch.diagonal(cov_clip, dim1=1, dim2=2).contiguous(), ymax)
+    U = torch.clamp(ei, min=eps)                                                   # fabolas.py:201-205
+    logP, dMu, dSg, dMM, info = eng.joint_min(mu, cov_clip)
+    assert int(info.cpu().numpy().max()) == 0
+    eng.es_setup(reps, cov, (logP, dMu, dSg, dMM), U, Omega)
+    ig, flag = eng.information_gain(cand)
+    assert int(flag.cpu().numpy().max()) == 0 and np.all(np.isfinite(ig.cpu().numpy()))
+    # oracle: same lists, the reference's algorithm restated (uses the C EPMGP oracle for p_min)
+    models = []
+    for b in range(B):
+        gp = go.GP(go.build_kernel(1, w["theta"][b], 6), mean=w["mean"]); gp.compute(w["X"], np.sqrt(w["yerr2"][b]))
+        models.append(gp)
+    pmin = [eo.joint_min(mu[b].cpu().numpy(), cov_clip[b].cpu().numpy(), with_derivatives=True) for b in range(B)]
+    for b in range(B):
+        assert np.max(np.abs(np.exp(pmin[b][0]) - np.exp(logP[b].cpu().numpy()))) < 1e-6
+    Om = [[Omega[b, p][:, None] for p in range(I)] for b in range(B)]
+    Ul = [U[b].cpu().numpy() for b in range(B)]
+    for x in (0, 7, 23):
+        ref = ao.information_gain(cand[x], models, pmin, list(reps), Ul, Om, {"y": w["y"]}, n_innovations=I)
+        assert abs(float(ig[x]) - ref) < 1e-6 * max(1.0, abs(ref))
