@@ -42,6 +42,7 @@ SIGNATURES = {
     "fab_epmgp_joint_min_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fab_es_setup": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int]),
     "fab_es_information_gain_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
+    "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
 }
@@ -275,6 +276,24 @@ class Engine:
         self._check(self.lib.fab_es_information_gain_batch(self._ctx, _ptr(Xc), M, _ptr(ig), _ptr(flag), _ptr(mm), _ptr(mv)),
                     "fab_es_information_gain_batch")
         return (ig, flag, mm, mv) if return_mixture else (ig, flag)
+
+    def kernel_matrix(self, family: int, theta, Xa, Xb=None, amp_mult: Optional[float] = None, nu_code: int = 0,
+                      grad: bool = False):
+        """K (B, Na, Nb) [, dK (B, Na, Nb, Pk)] of k(Xa, Xb) for every row of theta."""
+        Xa = self.tensor(Xa)
+        Xb = Xa if Xb is None else self.tensor(Xb)
+        theta = self.tensor(theta)
+        if theta.dim() == 1:
+            theta = theta[None]
+        B, Pk = theta.shape
+        Na, D = Xa.shape
+        Nb = Xb.shape[0]
+        amp_mult = float(D if amp_mult is None else amp_mult)
+        K = self.empty(B, Na, Nb)
+        dK = self.empty(B, Na, Nb, Pk) if grad else None
+        self._check(self.lib.fab_kernel_matrix(self._ctx, family, nu_code, _ptr(theta), B, _ptr(Xa), Na, _ptr(Xb), Nb, D,
+                                               amp_mult, _ptr(K), _ptr(dK)), "fab_kernel_matrix")
+        return (K, dK) if grad else K
 
     def debug_factor(self, b: int) -> torch.Tensor:
         L = self.empty(self.N, self.N)

@@ -1,0 +1,102 @@
+"""Entropy Search candidate search on the CUDA engine (reference: entropy_search.py), Matern-only
+kernel, no dataset-size dimension.  Quirk numbers refer to SURVEY.md section 3.4."""
+import logging
+import time
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+
+from . import epmgp, runtime
+from .acquisitions import information_gain, information_gain_batch, prepare_entropy_search
+from ._capi import FAB_FAMILY_M52
+from .fabolas import lognorm_logpdf
+from .horseshoe import Horseshoe
+from .models import ModelBatch
+from .sampler import EnsembleSampler
+
+
+def log_prob_batch(theta, engine):
+    """entropy_search.py:40-77 for a (B, P) block of walkers: box 0 < cov < 100, -9 < lamb < 2,
+    lognormal + horseshoe priors, set_parameter_vector([cov, *lamb]) (Q3), yerr = sqrt(noise)."""
+    theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    cov, lamb, noise = theta[:, 0], theta[:, 1:-1], theta[:, -1]
+    ok = (cov > 0) & (cov < 100) & np.all(lamb > -9, axis=1) & np.all(lamb < 2, axis=1) & (noise > -20) & (noise < 20)
+    ok &= noise >= 0                                  # sqrt(noise) of a negative number: NaN -> exception -> -inf
+    out = np.full(theta.shape[0], -np.inf)
+    if not np.any(ok):
+        return out
+    p = theta[ok]
+    prior = lognorm_logpdf(p[:, 0], 1.0) + Horseshoe(scale=0.1).logpdf(p[:, -1])
+    ll, info = engine.loglik(p[:, :-1], p[:, -1])
+    ll = ll.cpu().numpy()
+    ll[info.cpu().numpy() != 0] = -np.inf
+    out[ok] = prior + ll
+    return out
+
+
+def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None):
+    """entropy_search.py:20-85."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    engine = engine or runtime.new_engine()
+    engine.set_data(FAB_FAMILY_M52, X, y, float(np.mean(y)), float(X.shape[1]))
+    ndim = X.shape[1] + 2
+    sampler = EnsembleSampler(K, ndim, log_prob_batch, args=[engine], vectorize=True)
+    state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, rstate0=np.random.get_state())
+    sampler.reset()
+    sampler.run_mcmc(state, iterations)
+    return sampler.chain[:, -1]
+
+
+def entropy_search(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_innovations=20, burn_in=100,
+                   iterations=500, maxiter=100):
+    """entropy_search.py:88-169."""
+    X = np.asarray(dataset["X"], dtype=np.float64)
+    y = np.asarray(dataset["y"], dtype=np.float64).reshape(-1)
+    D = X.shape[1]
+    logging.info("Sampling hypeparameters..")
+    h = sample_hypers(X, y, K=n_hyper_samples, burn_in=burn_in, iterations=iterations)
+    with np.errstate(all="ignore"):
+        theta = np.column_stack([np.log(h[:, 0] / D), h[:, 1:-1]])     # kernel_cov * Matern52(metric=e**lamb)
+    models = ModelBatch(FAB_FAMILY_M52, X, y, theta, h[:, -1] ** 2, amp_mult=D)   # Q3: compute(X, yerr=noise)
+    eng = models.engine
+    K = len(models)
+    reps = np.random.uniform(low=[b[0] for b in bounds], high=[b[1] for b in bounds], size=(K, n_gen_samples, D))
+    mean, _, cov = eng.predict(reps, want_var=True, want_cov=True)
+    y_max = np.empty(K)
+    for k in range(K):
+        Kk = eng.kernel_matrix(FAB_FAMILY_M52, theta[k], reps[k], amp_mult=D)[0].cpu().numpy()
+        Kk[np.diag_indices_from(Kk)] += 1.25e-12
+        y_max[k] = np.random.multivariate_normal(np.full(n_gen_samples, models.mean), Kk).max()   # Q5
+    U, _, _ = eng.expected_improvement(mean, torch.diagonal(cov, dim1=1, dim2=2).contiguous(), y_max)
+    p_min = epmgp.joint_min_batch(mean, cov, with_derivatives=True, engine=eng)
+    Omega = np.random.normal(size=(K, n_innovations, n_gen_samples))
+    prepare_entropy_search(models, reps, cov, p_min, U, Omega)
+    logging.info("Ready to optimize Information Gain")
+    return minimize(fun=lambda x: -information_gain(x, models), x0=X[np.argmax(y)], method="L-BFGS-B",
+                    bounds=bounds, options={"maxiter": maxiter})
+
+
+def es(obj_function, prior, bounds, iterations=10):
+    """entropy_search.py:172-229 without the hard-coded Colab save path."""
+    wallclock_time = time.time()
+    progress = {"config": np.empty((0, prior["X"].shape[1])), "value": np.empty((0, 1)), "time": np.empty((0, 1))}
+    for i in range(iterations):
+        logging.info(f"---- ES: Iteration #{i+1} ----")
+        result = None
+        while result is None:
+            try:
+                result = entropy_search(prior, bounds)
+            except ArithmeticError:
+                logging.warning("Bad surrogate, trying again..")
+        y = obj_function(result.x)
+        iteration_time = time.time() - wallclock_time
+        prior["X"] = np.vstack([prior["X"], result.x])
+        prior["y"] = np.vstack([np.asarray(prior["y"]).reshape(-1, 1), np.array([[y]])])
+        progress["config"] = np.vstack([progress["config"], result.x])
+        progress["value"] = np.vstack([progress["value"], np.array([[y]])])
+        progress["time"] = np.vstack([progress["time"], np.array([[iteration_time]])])
+    prior["y_best"] = max(prior["y"])
+    prior["X_best"] = prior["X"][np.argmax(prior["y"])]
+    return prior, progress

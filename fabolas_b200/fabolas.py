@@ -1,0 +1,186 @@
+"""FABOLAS candidate search on the CUDA engine: same functions, arguments and quirks as the
+reference's fabolas.py, with the MCMC likelihood, model fitting, EPMGP and information gain
+evaluated in batches on the GPU.  Quirk numbers refer to SURVEY.md section 3.4."""
+import logging
+import time
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+
+from . import epmgp, runtime
+from .acquisitions import information_gain_cost, information_gain_cost_batch, prepare_entropy_search
+from ._capi import FAB_FAMILY_M52_BASIS
+from .george import GP, ConstantKernel, LinearKernel, Matern52Kernel
+from .horseshoe import Horseshoe
+from .models import ModelBatch
+from .sampler import EnsembleSampler
+
+
+def lognorm_logpdf(x, s=1.0):
+    """scipy.stats.lognorm.logpdf(x, s, 0) for x > 0 (fabolas.py:47)."""
+    with np.errstate(all="ignore"):
+        return -np.log(s * x * np.sqrt(2 * np.pi)) - np.log(x) ** 2 / (2 * s * s)
+
+
+def log_likelihood(params, gp, X, y):
+    """fabolas.py:16-66, one walker, george-shaped GP facade."""
+    cov, lamb, noise = params[0], params[1:-1], params[-1]
+    if not 0 < cov < 20:
+        return -np.inf
+    if not (np.all(np.array(lamb) > -9) and np.all(np.array(lamb) < 2)):
+        return -np.inf
+    if not -20 < noise < 20:
+        return -np.inf
+    prior = lognorm_logpdf(cov, 1.0) + Horseshoe(scale=0.1).logpdf(noise)
+    gp.kernel.set_parameter_vector([cov, *(np.e ** lamb[:-2]), *lamb[-2:]])      # Q1
+    try:
+        if noise < 0:
+            return -np.inf
+        gp.compute(X, yerr=np.sqrt(noise))
+    except Exception:
+        return -np.inf
+    return prior + gp.log_likelihood(y.reshape(-1), quiet=True)
+
+
+def log_likelihood_batch(params, engine):
+    """The same function for a (B, P) block of walkers in one GPU call (engine holds X, y)."""
+    params = np.atleast_2d(np.asarray(params, dtype=np.float64))
+    cov, lamb, noise = params[:, 0], params[:, 1:-1], params[:, -1]
+    ok = (cov > 0) & (cov < 20) & np.all(lamb > -9, axis=1) & np.all(lamb < 2, axis=1) & (noise > -20) & (noise < 20)
+    ok &= ~(noise < 0)
+    out = np.full(params.shape[0], -np.inf)
+    if not np.any(ok):
+        return out
+    p = params[ok]
+    prior = lognorm_logpdf(p[:, 0], 1.0) + Horseshoe(scale=0.1).logpdf(p[:, -1])
+    theta = np.column_stack([p[:, 0], np.e ** p[:, 1:-3], p[:, -3:-1]])          # Q1: raw cov, e**lamb, raw basis params
+    ll, info = engine.loglik(theta, p[:, -1])                                    # yerr = sqrt(noise) -> yerr^2 = noise
+    ll = ll.cpu().numpy()
+    ll[info.cpu().numpy() != 0] = -np.inf
+    out[ok] = prior + ll
+    return out
+
+
+def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None):
+    """fabolas.py:69-117: K walkers, 100 burn-in + 500 steps, last positions (K, P)."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    engine = engine or runtime.new_engine()
+    # kernel = 1 * Matern52(axes 0..d-1) * (Linear(axis d) + Constant(axis d)); the scalar becomes a
+    # ConstantKernel over all ndim axes, hence amp_mult = ndim
+    engine.set_data(FAB_FAMILY_M52_BASIS, X, y, float(np.mean(y)), float(X.shape[1]))
+    ndim = X.shape[1] + 3                      # len(kernel) + 1
+    sampler = EnsembleSampler(K, ndim, log_likelihood_batch, args=[engine], vectorize=True)
+    state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, rstate0=np.random.get_state())
+    sampler.reset()
+    sampler.run_mcmc(state, iterations)
+    return sampler.chain[:, -1]
+
+
+def _model_theta(hypers, ndim):
+    """Q2: models are rebuilt as cov * Matern52(metric=e**lamb) * (Linear(lamb[-2]) + Constant(lamb[-1]))."""
+    h = np.atleast_2d(hypers)
+    with np.errstate(all="ignore"):
+        return np.column_stack([np.log(h[:, 0] / ndim), h[:, 1:-3], h[:, -3:-1]]), h[:, -1]
+
+
+def get_candidate(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_innovations=20, batched_fd=False,
+                  burn_in=100, iterations=500, maxiter=None):
+    """fabolas.py:120-264."""
+    if len(dataset["size"].shape) == 1:
+        dataset["size"] = dataset["size"].reshape(-1, 1)
+    X = np.concatenate([dataset["X"], dataset["size"]], axis=1)
+    Xf = np.concatenate((X[:, :-1], ((1 - X[:, -1]) ** 2).reshape(-1, 1)), axis=1)    # Q4
+    D = X.shape[1]
+
+    logging.info("Sampling hyperparameters for function models...")
+    hypers = sample_hypers(Xf, dataset["y"], K=n_hyper_samples, burn_in=burn_in, iterations=iterations)
+    logging.info("Sampling hyperparameters for cost models...")
+    cost_hypers = sample_hypers(X, dataset["c"], K=n_hyper_samples, burn_in=burn_in, iterations=iterations)
+
+    theta, noise = _model_theta(hypers, D)
+    models = ModelBatch(FAB_FAMILY_M52_BASIS, Xf, dataset["y"], theta, noise, amp_mult=D)   # yerr = sqrt(noise)
+    eng = models.engine
+    K = len(models)
+    reps = np.random.uniform(low=[b[0] for b in bounds], high=[b[1] for b in bounds], size=(K, n_gen_samples, D))
+    mean, _, cov = eng.predict(reps, want_var=True, want_cov=True)
+    eps = np.finfo(np.float64).eps
+    cov_clip = torch.clamp(cov, min=eps)                                               # Q6
+    # incumbent of EI = max of a PRIOR draw at the representers (Q5)
+    y_max = np.empty(K)
+    for k in range(K):
+        Kk = eng.kernel_matrix(FAB_FAMILY_M52_BASIS, theta[k], reps[k], amp_mult=D)[0].cpu().numpy()
+        Kk[np.diag_indices_from(Kk)] += 1.25e-12
+        y_max[k] = np.random.multivariate_normal(np.full(n_gen_samples, models.mean), Kk).max()
+    var_reps = torch.diagonal(cov_clip, dim1=1, dim2=2).contiguous()
+    ei, _, _ = eng.expected_improvement(mean, var_reps, y_max)
+    U = torch.clamp(ei, min=eps)
+    logging.debug("Computing pMin")
+    p_min = epmgp.joint_min_batch(mean, cov_clip, with_derivatives=True, engine=eng)
+    Omega = np.random.normal(size=(K, n_innovations, n_gen_samples))
+    prepare_entropy_search(models, reps, cov, p_min, U, Omega)
+
+    ctheta, cnoise = _model_theta(cost_hypers, D)
+    cost_models = ModelBatch(FAB_FAMILY_M52_BASIS, X, dataset["c"], ctheta, cnoise, amp_mult=D)
+
+    logging.info("Ready to optimize Information Gain by Cost")
+    imax = np.argmax(dataset["y"])
+    starting_point = np.concatenate([dataset["X"][imax], dataset["size"][imax]])
+    opts = {} if maxiter is None else {"maxiter": maxiter}
+    if batched_fd:
+        # feed L-BFGS-B value and forward-difference gradient from ONE batched call
+        def fun(x, h=1e-8):
+            pts = np.vstack([x] + [x + h * e for e in np.eye(len(x))])
+            v = -information_gain_cost_batch(pts, cost_models, models)
+            return v[0], (v[1:] - v[0]) / h
+        return minimize(fun=fun, x0=starting_point, jac=True, method="L-BFGS-B", bounds=bounds, options=opts)
+    return minimize(fun=lambda x: -information_gain_cost(x, cost_models, models), x0=starting_point,
+                    method="L-BFGS-B", bounds=bounds, options=opts)
+
+
+def fabolas(obj_function, prior, bounds, iterations=10, **kwargs):
+    """fabolas.py:267-327 (outer loop; the objective is the expensive black box, not the path)."""
+    prior["min_time"] = 0
+    if min(prior["c"]) < 0:
+        prior["min_time"] = np.array(min(prior["c"]))
+        prior["c"] += -prior["min_time"]
+    wallclock_time = time.time()
+    progress = {"config": np.empty((0, prior["X"].shape[1] + 1)), "value": np.empty((0, 1)),
+                "time": np.empty((0, 1)), "size": np.empty((0, 1))}
+    for i in range(iterations):
+        logging.info(f"---- FABOLAS: Iteration #{i+1} ----")
+        result = None
+        while result is None:
+            try:
+                result = get_candidate(prior, bounds, **kwargs)
+            except ArithmeticError:
+                logging.warning("Bad surrogate, trying again..")
+        logging.info(f"Evaluating function at {result.x}")
+        cost = time.time()
+        y = obj_function(result.x)
+        cost = time.time() - cost
+        iteration_time = time.time() - wallclock_time
+        prior["X"] = np.vstack([prior["X"], result.x[:-1]])
+        prior["y"] = np.append(prior["y"], np.array([y]))
+        prior["size"] = np.append(prior["size"], np.array([result.x[-1]]))
+        prior["c"] = np.append(prior["c"], np.array([np.log10(cost) - prior["min_time"]]))
+        if min(prior["c"]) < 0:
+            prior["c"] += -(np.log10(cost) - prior["min_time"])
+            prior["min_time"] = np.array(np.log10(cost))
+        progress["config"] = np.vstack([progress["config"], result.x])
+        progress["value"] = np.append(progress["value"], np.array([y]))
+        progress["time"] = np.append(progress["time"], np.array([iteration_time]))
+        progress["size"] = np.append(progress["size"], np.array([result.x[-1]]))
+    prior["y_best"] = max(prior["y"])
+    prior["X_best"] = prior["X"][np.argmax(prior["y"])]
+    return prior, progress
+
+
+def make_gp(X, mean):
+    """The george kernel/GP pair of fabolas.py:81-99 (single-model facade; used by log_likelihood)."""
+    nd = X.shape[1]
+    kernel = 1 * Matern52Kernel(metric=np.ones(nd - 1) * 0.1, ndim=nd, axes=list(range(nd - 1))) * (
+        LinearKernel(log_gamma2=np.log(1), order=1, ndim=nd, axes=[nd - 1])
+        + ConstantKernel(log_constant=np.log(1), ndim=nd, axes=[nd - 1]))
+    return GP(kernel=kernel, mean=mean)

@@ -124,6 +124,14 @@ int fab_es_setup(fab_ctx* ctx, const double* reps, int Z, const double* cov_reps
 int fab_es_information_gain_batch(fab_ctx* ctx, const double* Xc, int M, double* ig, int* nan_flag,
                                   double* mix_mean, double* mix_var);
 
+/* Materialised covariance matrices k(Xa, Xb) for B hyper-parameter rows (and, optionally, their
+ * derivatives with respect to every theta_k): the kernel object surface of ard.py
+ * (AutomaticRelevanceDetermination.__call__, ard.py:82-180: nu_code 0 = 2.5, 1 = 1.5, 2 = 0.5, 3 = inf
+ * on r2 = sum_k (x_k - x'_k)^2 / M_k) and george's kernel.get_value / get_gradient.
+ *   Xa Na x D, Xb Nb x D, theta B x Pk  ->  K B x Na x Nb ; dK B x Na x Nb x Pk or NULL.           */
+int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta, int B, const double* Xa,
+                      int Na, const double* Xb, int Nb, int D, double amp_mult, double* K, double* dK);
+
 /* Debug / test access: copy the dense lower Cholesky factor of walker b (N x N row-major, device)
  * out of the tiled workspace left by the last fab_gp_loglik_batch(grad != NULL) / factorize call. */
 int fab_gp_debug_get_factor(fab_ctx* ctx, int b, double* L_out);

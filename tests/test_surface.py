@@ -1,0 +1,235 @@
+"""The reference-shaped Python surface (george facade, sampler, fabolas / entropy_search /
+expected_improvement / acquisitions / epmgp / horseshoe / ard modules) on top of the engine.
+CPU tier: engines are backed by the kernel emulator; GPU tier: the real library."""
+import numpy as np
+import pytest
+
+from oracle import acq_oracle as ao
+from oracle import george_oracle as go
+from tests.conftest import golden
+
+
+@pytest.fixture()
+def sim_runtime():
+    from tests.cusim.build_sim import build_sim
+    from fabolas_b200 import Engine, runtime
+    lib = build_sim()
+    runtime.set_engine_factory(lambda: Engine(device="cpu", lib_path=lib))
+    yield runtime
+    runtime.set_engine_factory(None)
+
+
+@pytest.fixture()
+def gpu_runtime():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fabolas_b200 import runtime
+    from fabolas_b200.build import build
+    build()
+    runtime.set_engine_factory(None)
+    yield runtime
+
+
+def _toy(N=14, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, (N, 2)); s = rng.uniform(0.1, 1, N)
+    y = np.sin(2 * X[:, 0]) * (0.5 + s) + 0.3 * X[:, 1]
+    c = 1 + 2 * s + 0.05 * rng.standard_normal(N)
+    return X, s, y, c
+
+
+def _george_facade(rt):
+    from fabolas_b200 import george as fg
+    X, s, y, _ = _toy()
+    Xf = np.column_stack([X, (1 - s) ** 2])
+    k = 2.0 * fg.Matern52Kernel(metric=[0.5, 0.8], ndim=3, axes=[0, 1]) * (
+        fg.LinearKernel(log_gamma2=0.1, order=1, ndim=3, axes=[2]) + fg.ConstantKernel(log_constant=-0.2, ndim=3, axes=[2]))
+    ko = 2.0 * go.Matern52Kernel([0.5, 0.8], ndim=3, axes=[0, 1]) * (
+        go.LinearKernel(0.1, order=1, ndim=3, axes=[2]) + go.ConstantKernel(-0.2, ndim=3, axes=[2]))
+    assert len(k) == 5 and k.ndim == 3
+    assert np.allclose(k.get_parameter_vector(), ko.get_parameter_vector())
+    assert np.allclose(k.get_value(Xf), ko.get_value(Xf), rtol=1e-12)
+    gp, gpo = fg.GP(k, mean=y.mean()), go.GP(ko, mean=y.mean())
+    gp.compute(Xf, yerr=0.1); gpo.compute(Xf, 0.1)
+    assert abs(gp.log_likelihood(y, quiet=True) - gpo.log_likelihood(y)) < 1e-9 * abs(gpo.log_likelihood(y))
+    assert np.allclose(gp.grad_log_likelihood(y), gpo.grad_log_likelihood(y), rtol=1e-8, atol=1e-9)
+    T = np.random.default_rng(1).uniform(0, 1, (5, 3))
+    mu, cov = gp.predict(y, T, return_cov=True); muo, covo = gpo.predict(y, T, return_cov=True)
+    assert np.allclose(mu, muo, rtol=1e-9, atol=1e-11) and np.allclose(cov, covo, rtol=1e-8, atol=1e-10)
+    v = np.array([0.3, -0.1, 0.2, 0.0, 0.4])
+    k.set_parameter_vector(v); ko.set_parameter_vector(v)
+    gp.compute(Xf, 0.05); gpo.compute(Xf, 0.05)
+    assert abs(gp.log_likelihood(y) - gpo.log_likelihood(y)) < 1e-9 * abs(gpo.log_likelihood(y))
+    assert gp.sample(T).shape == (5,)
+    # the reference's try/except contract: not positive definite -> exception from compute, -inf with quiet
+    Xd = Xf.copy(); Xd[1:8] = Xd[0]                       # 8 identical observations, huge amplitude, no jitter
+    k.set_parameter_vector([15.0, 0.0, 0.0, 0.0, 0.0])
+    gp2 = fg.GP(k, mean=0.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp2.compute(Xd, yerr=0.0)
+        gp2.log_likelihood(y)
+    with pytest.raises(NotImplementedError):
+        fg.compile_kernel(fg.LinearKernel(0.0, ndim=2) + fg.ConstantKernel(0.0, ndim=2))
+
+
+def test_george_facade_emulated(sim_runtime):
+    _george_facade(sim_runtime)
+
+
+@pytest.mark.gpu
+def test_george_facade_gpu(gpu_runtime):
+    _george_facade(gpu_runtime)
+
+
+def _loglik_functions(rt):
+    """fabolas.log_likelihood (one walker, facade) == log_likelihood_batch == oracle prior + oracle GP."""
+    from fabolas_b200 import fabolas as ff, entropy_search as fe
+    X, s, y, _ = _toy()
+    Xf = np.column_stack([X, (1 - s) ** 2])
+    rng = np.random.default_rng(2)
+    P = rng.uniform(0.05, 0.9, (6, 6))
+    P[1, 0] = 25.0; P[2, 2] = 2.5; P[3, -1] = -0.1           # outside the box / negative noise -> -inf
+    eng = rt.new_engine()
+    eng.set_data(1, Xf, y, float(y.mean()), 3.0)
+    batch = ff.log_likelihood_batch(P, eng)
+    gp = ff.make_gp(Xf, float(y.mean()))
+    one = np.array([ff.log_likelihood(p, gp, Xf, y) for p in P])
+    ref = []
+    for p in P:
+        pr = ao.fabolas_log_prior(p)
+        if not np.isfinite(pr):
+            ref.append(-np.inf); continue
+        th, n = ao.fabolas_theta(p)
+        ref.append(pr + go.loglik_batch(1, Xf, y, y.mean(), th[None], np.array([n]))[0])
+    ref = np.array(ref)
+    fin = np.isfinite(ref)
+    assert np.array_equal(fin, np.isfinite(batch)) and np.array_equal(fin, np.isfinite(one)) and fin.sum() == 3
+    assert np.allclose(batch[fin], ref[fin], rtol=1e-9) and np.allclose(one[fin], ref[fin], rtol=1e-9)
+    # Entropy-Search flavour
+    eng.set_data(0, X, y, float(y.mean()), 2.0)
+    Q = rng.uniform(0.05, 0.9, (4, 4)); Q[0, 0] = 120.0
+    lp = fe.log_prob_batch(Q, eng)
+    assert lp[0] == -np.inf
+    for q, v in zip(Q[1:], lp[1:]):
+        r = ao.lognorm_logpdf(q[0]) + ao.horseshoe_logpdf(q[-1]) + go.loglik_batch(0, X, y, y.mean(), q[None, :-1], q[-1:])[0]
+        assert abs(v - r) < 1e-9 * abs(r)
+
+
+def test_loglik_functions_emulated(sim_runtime):
+    _loglik_functions(sim_runtime)
+
+
+@pytest.mark.gpu
+def test_loglik_functions_gpu(gpu_runtime):
+    _loglik_functions(gpu_runtime)
+
+
+def test_sampler_targets_known_distribution():
+    """Stretch move on a correlated 3-d Gaussian: moments recovered (no engine involved)."""
+    from fabolas_b200.sampler import EnsembleSampler
+    np.random.seed(0)
+    C = np.array([[1.0, 0.6, 0.0], [0.6, 2.0, -0.3], [0.0, -0.3, 0.5]]); Ci = np.linalg.inv(C)
+    lp = lambda x: -0.5 * np.einsum("bi,ij,bj->b", x, Ci, x)
+    s = EnsembleSampler(40, 3, lp, vectorize=True)
+    st = s.run_mcmc(np.random.randn(40, 3), 300, rstate0=np.random.get_state())
+    s.reset()
+    s.run_mcmc(st, 1500)
+    flat = s.get_chain().reshape(-1, 3)
+    assert s.chain.shape == (40, 1500, 3) and s.chain[:, -1].shape == (40, 3)
+    assert np.all(np.abs(flat.mean(0)) < 0.15) and np.allclose(np.cov(flat.T), C, atol=0.25)
+    assert 0.2 < s.acceptance_fraction.mean() < 0.9
+    with pytest.raises(ValueError):
+        EnsembleSampler(4, 2, lambda x: np.full(len(x), np.nan), vectorize=True).run_mcmc(np.random.rand(4, 2), 1)
+
+
+def test_candidate_searches_run_emulated(sim_runtime):
+    from fabolas_b200 import fabolas as ff, entropy_search as fe, expected_improvement as fei
+    np.random.seed(3)
+    X, s, y, c = _toy(12)
+    ds = {"X": X.copy(), "y": y.copy(), "size": s.copy(), "c": c.copy()}
+    bounds = [(-1, 1), (-1, 1), (1 / 256, 1)]
+    r = ff.get_candidate(ds, bounds, n_hyper_samples=4, n_gen_samples=6, n_innovations=3, burn_in=2, iterations=3, maxiter=2)
+    assert r.x.shape == (3,) and all(lo <= v <= hi for v, (lo, hi) in zip(r.x, bounds)) and np.isfinite(r.fun)
+    r2 = fe.entropy_search({"X": X, "y": y}, bounds[:2], n_hyper_samples=4, n_gen_samples=6, n_innovations=3,
+                           burn_in=2, iterations=3, maxiter=2)
+    assert r2.x.shape == (2,) and np.isfinite(r2.fun)
+    xc = fei.get_candidate({"X": X, "y": y}, bounds[:2], n_gen_samples=30)
+    assert xc.shape == (2,)
+
+
+def _ei_fit_matches_sklearn(rt):
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import Matern
+    from fabolas_b200 import expected_improvement as fei
+    X, s, y, _ = _toy(25, seed=4)
+    gpr = GaussianProcessRegressor(kernel=1 * Matern(nu=5 / 2, length_scale_bounds=(1e-10, 1e10))).fit(X, y)
+    eng = rt.new_engine()
+    theta, lml = fei.fit_gpr(eng, X, y)
+    assert abs(lml - gpr.log_marginal_likelihood_value_) < 1e-6 * max(1, abs(lml))
+    assert np.allclose(theta, gpr.kernel_.theta, rtol=1e-3, atol=1e-3)
+    T = np.random.default_rng(5).uniform(-1, 1, (40, 2))
+    mu, var = eng.predict(T)
+    m2, s2 = gpr.predict(T, return_std=True)
+    assert np.allclose(mu[0].cpu().numpy(), m2, atol=1e-5) and np.allclose(var[0].cpu().numpy(), s2 ** 2, atol=1e-5)
+
+
+def test_ei_fit_matches_sklearn_emulated(sim_runtime):
+    _ei_fit_matches_sklearn(sim_runtime)
+
+
+@pytest.mark.gpu
+def test_ei_fit_matches_sklearn_gpu(gpu_runtime):
+    _ei_fit_matches_sklearn(gpu_runtime)
+
+
+def _ard_and_epmgp_and_horseshoe(rt):
+    from fabolas_b200.ard import AutomaticRelevanceDetermination
+    from fabolas_b200 import epmgp as fep
+    from fabolas_b200.horseshoe import Horseshoe
+    g = golden("ard_ref.npz")
+    for n in (2, 4, 6):
+        X, Y, ls = g[f"n{n}_X"], g[f"n{n}_Y"], g[f"n{n}_ls"]
+        for nu in (0.5, 1.5, 2.5, np.inf):
+            k = AutomaticRelevanceDetermination(length_scale=ls, nu=nu)
+            tag = f"n{n}_nu{nu}"
+            assert np.allclose(k(X, Y), g[tag + "_Kxy"], rtol=1e-11, atol=1e-14)
+            if nu != 0.5:
+                K, G = k(X, eval_gradient=True)
+                assert np.allclose(K, g[tag + "_K"], rtol=1e-11, atol=1e-14)
+                assert np.allclose(G, g[tag + "_G"], rtol=1e-10, atol=1e-13)
+    assert "AutomaticRelevanceDetermination(length_scale=[" in repr(AutomaticRelevanceDetermination([1.0, 2.0], nu=2.5))
+    ge = golden("epmgp_ref.npz")
+    logP, dMu, dSg, dMM = fep.joint_min(ge["z12_mu"], ge["z12_S"], with_derivatives=True)
+    assert np.max(np.abs(np.exp(logP) - np.exp(ge["z12_logP"]))) < 1e-6 and np.allclose(dMM, ge["z12_dMM"], atol=1e-9)
+    assert np.allclose(fep.joint_min(ge["z12_mu"], ge["z12_S"]), logP)
+    gp = golden("priors_ref.npz")
+    h = Horseshoe(scale=0.1)
+    for x, ref in zip(gp["xs"], gp["horseshoe01"]):
+        v = h.logpdf(x)
+        assert (np.isinf(ref) and v == ref) or abs(v - ref) <= 1e-12 * max(1.0, abs(ref))
+    assert np.allclose(h.logpdf(gp["xs"]), gp["horseshoe01"], rtol=1e-12, equal_nan=True)
+
+
+def test_ard_epmgp_horseshoe_emulated(sim_runtime):
+    _ard_and_epmgp_and_horseshoe(sim_runtime)
+
+
+@pytest.mark.gpu
+def test_ard_epmgp_horseshoe_gpu(gpu_runtime):
+    _ard_and_epmgp_and_horseshoe(gpu_runtime)
+
+
+@pytest.mark.gpu
+def test_fabolas_get_candidate_gpu(gpu_runtime):
+    """One full FABOLAS candidate search on the reference's svm_mnist prior (N=100, D=3), with the
+    reference's K=20 / Z=50 / I=20 and a shortened chain."""
+    import pandas as pd  # noqa: F401  (same loader logic as svm_mnist.load_prior; CSV is not on the GPU box)
+    from fabolas_b200 import fabolas as ff
+    np.random.seed(1)
+    g = golden("gp_oracle_svm_mnist.npz")
+    X = g["X"][:, :2]; s = 1 - np.sqrt(g["X"][:, 2])
+    ds = {"X": X.copy(), "y": g["y"].copy(), "size": s.copy(), "c": np.log10(1 + 100 * s) + 0.5}
+    bounds = [(-10, 10), (-10, 10), (1 / 256, 1)]
+    r = ff.get_candidate(ds, bounds, burn_in=20, iterations=40, maxiter=5, batched_fd=True)
+    assert r.x.shape == (3,) and np.isfinite(r.fun) and all(lo <= v <= hi for v, (lo, hi) in zip(r.x, bounds))
