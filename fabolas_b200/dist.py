@@ -1,0 +1,104 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed (NCCL over NVLink 5 /
+NVSwitch on the B200 box; gloo in the CPU tests) for the plumbing.
+
+The path shards without any data-path exchange: walkers / hyper-samples are
+split contiguously across ranks for the likelihood, candidates for prediction / EI / information
+gain; X, y and the factorised models are replicated.  The only collectives are an all-gather of
+the per-walker log-likelihoods (+ gradients), 8 B (+ 8 B P) bytes per walker, once per stretch
+half-step, and an all-gather of one (value, index) pair per rank for the acquisition argmax."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, size: int):
+    """Contiguous split of range(n): first n % size ranks get one extra item."""
+    base, extra = divmod(n, size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _allgather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """All-gather of the row shards produced by shard_range (uneven shards are padded)."""
+    rank, size = world()
+    if size == 1:
+        return local
+    per = -(-n_total // size)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((size * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    parts = []
+    for r in range(size):
+        lo, hi = shard_range(n_total, r, size)
+        parts.append(out[r * per: r * per + (hi - lo)])
+    return torch.cat(parts, 0)
+
+
+def sharded_loglik(engine, theta, yerr2, grad: bool = False):
+    """ll (B,), [grad (B, Pk+1),] info (B,) for the FULL batch on every rank; each rank evaluates its
+    contiguous shard of the walkers on its own GPU."""
+    rank, size = world()
+    theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    yerr2 = np.asarray(yerr2, dtype=np.float64).reshape(-1)
+    B = theta.shape[0]
+    lo, hi = shard_range(B, rank, size)
+    if hi > lo:
+        out = engine.loglik(theta[lo:hi], yerr2[lo:hi], grad=grad)
+    else:
+        out = (engine.empty(0), engine.empty(0, engine.Pk + 1), engine.empty(0, dtype=torch.int32)) if grad else \
+              (engine.empty(0), engine.empty(0, dtype=torch.int32))
+    return tuple(_allgather_rows(t, B) for t in out)
+
+
+def sharded_argmax(values: torch.Tensor, offset: int):
+    """Global (max value, global index) from per-rank candidate shards: all-gather of one pair per
+    rank, first occurrence wins (np.argmax semantics)."""
+    rank, size = world()
+    if values.numel():
+        v, i = torch.max(values, dim=0)
+        pair = torch.stack([v.double(), (i + offset).double()])
+    else:
+        pair = torch.tensor([-float("inf"), -1.0], dtype=torch.float64, device=values.device)
+    if size == 1:
+        return float(pair[0]), int(pair[1])
+    allp = torch.empty(size * 2, dtype=torch.float64, device=values.device)
+    dist.all_gather_into_tensor(allp, pair)
+    allp = allp.view(size, 2).cpu().numpy()
+    best = max(range(size), key=lambda r: (allp[r, 0], -allp[r, 1] if allp[r, 1] >= 0 else -np.inf))
+    return float(allp[best, 0]), int(allp[best, 1])
+
+
+def sharded_ei_argmax(engine, T, y_max, xi: float = 0.0):
+    """expected_improvement.get_candidate's sweep (predict -> EI -> argmax) with the M candidates of T
+    sharded across ranks; the models are resident (replicated) on every rank.  Model 0 decides."""
+    rank, size = world()
+    T = np.atleast_2d(np.asarray(T, dtype=np.float64))
+    lo, hi = shard_range(T.shape[0], rank, size)
+    if hi > lo:
+        mu, var = engine.predict(T[lo:hi], want_var=True)
+        ei, _, _ = engine.expected_improvement(mu[:1], var[:1], np.array([y_max]), xi=xi)
+        vals = ei[0]
+    else:
+        vals = engine.empty(0)
+    return sharded_argmax(vals, lo)
+
+
+def sharded_information_gain(engine, Xc):
+    """Information gain of every row of Xc on every rank; candidates sharded across ranks."""
+    rank, size = world()
+    Xc = np.atleast_2d(np.asarray(Xc, dtype=np.float64))
+    lo, hi = shard_range(Xc.shape[0], rank, size)
+    if hi > lo:
+        ig, flag = engine.information_gain(Xc[lo:hi])
+    else:
+        ig, flag = engine.empty(0), engine.empty(0, dtype=torch.int32)
+    return _allgather_rows(ig, Xc.shape[0]), _allgather_rows(flag, Xc.shape[0])

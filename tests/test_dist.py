@@ -1,0 +1,56 @@
+"""Multi-process sharding (world_size 2, gloo, CPU): the N > 1 host logic of fabolas_b200.dist with
+emulator-backed engines.  The GPU box runs the same code over NCCL (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, size, port, lib, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from fabolas_b200 import Engine
+        from fabolas_b200 import dist as fd
+        rng = np.random.default_rng(0)                     # identical inputs on every rank
+        N, D, B = 20, 3, 5                                 # 5 walkers over 2 ranks: uneven shards
+        X = rng.uniform(-1, 1, (N, D)); X[:, -1] = rng.uniform(0, 1, N)
+        y = np.sin(X.sum(1))
+        theta = rng.uniform(-1, 1, (B, D + 2)); yerr2 = rng.uniform(1e-3, 0.1, B)
+        eng = Engine(device="cpu", lib_path=lib)
+        eng.set_data(1, X, y, float(y.mean()), D)
+        ll, g, info = fd.sharded_loglik(eng, theta, yerr2, grad=True)
+        ll1, g1, _ = eng.loglik(theta, yerr2, grad=True)
+        assert ll.shape == (B,) and g.shape == (B, D + 3) and int(info.abs().sum()) == 0
+        assert torch.equal(ll, ll1) and torch.equal(g, g1)
+        # candidate sharding + argmax all-gather
+        eng.fit(theta[:2], yerr2[:2])
+        T = rng.uniform(0, 1, (37, D))
+        val, idx = fd.sharded_ei_argmax(eng, T, float(y.max()))
+        mu, var = eng.predict(T)
+        ei, bv, bi = eng.expected_improvement(mu[:1], var[:1], np.array([y.max()]))
+        assert idx == int(bi[0]) and abs(val - float(bv[0])) < 1e-15
+        assert fd.shard_range(5, 0, 2) == (0, 3) and fd.shard_range(5, 1, 2) == (3, 5)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_paths_world2_gloo():
+    from tests.cusim.build_sim import build_sim
+    lib = build_sim()
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lib, out)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs) and len(out) == 2
