@@ -44,6 +44,7 @@ SIGNATURES = {
     "fab_es_information_gain_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
+    "fab_ctx_debug_set_max_slots": (_c_int, [_vp, _c_int]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
 }
 
@@ -128,6 +129,9 @@ class Engine:
 
     def set_timing(self, enable: bool):
         self._check(self.lib.fab_ctx_set_timing(self._ctx, int(enable)), "fab_ctx_set_timing")
+
+    def debug_set_max_slots(self, n: int):
+        self._check(self.lib.fab_ctx_debug_set_max_slots(self._ctx, n), "fab_ctx_debug_set_max_slots")
 
     def get_timing(self):
         """Durations (ms) of the kernels launched by the most recent batched call."""

@@ -41,6 +41,7 @@ struct fab_ctx {
     bool factored = false;
     bool inverted = false;  // workspace holds W = L^-1 (and alpha) instead of L
     int smem_optin = 232448;
+    int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -135,6 +136,12 @@ int fab_ctx_destroy(fab_ctx* c) {
     return FAB_OK;
 }
 
+int fab_ctx_debug_set_max_slots(fab_ctx* c, int n) {
+    if (!c || n < 4 || n > MAX_SLOTS) return FAB_EINVAL;
+    c->max_slots = n;
+    return FAB_OK;
+}
+
 int fab_ctx_set_timing(fab_ctx* c, int enable) {
     if (!c) return FAB_EINVAL;
 #ifndef FAB_CUSIM
@@ -191,7 +198,7 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
     const GpData& gd = c->gd;
     const int ntiles = gd.NT * (gd.NT + 1) / 2;
     // slots: everything if it fits, else as many as shared memory allows (>= 4 needed)
-    int nslot = ntiles < MAX_SLOTS ? ntiles : MAX_SLOTS;
+    int nslot = ntiles < c->max_slots ? ntiles : c->max_slots;
     while (nslot > 0 && factor_smem_bytes(nslot, gd.Np, gd.d) > (size_t)c->smem_optin) --nslot;
     const bool fits = nslot >= ntiles;
     if (nslot < 4 && !fits) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA factor kernel");
@@ -223,7 +230,7 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
 static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int B, double* grad, const int* info) {
     const GpData& gd = c->gd;
     const int ntiles = gd.NT * (gd.NT + 1) / 2;
-    int nslot = MAX_SLOTS;
+    int nslot = c->max_slots;
     while (nslot > 0 && grad_smem_bytes(nslot, gd.Np, gd.d) > (size_t)c->smem_optin) --nslot;
     if (nslot > 2 * ntiles) nslot = 2 * ntiles;
     if (nslot < 4 && nslot < 2 * ntiles) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA gradient kernel");

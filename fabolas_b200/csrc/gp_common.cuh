@@ -51,12 +51,46 @@ __device__ __forceinline__ Hyper decode_hyper(const GpData& gd, const double* __
     return h;
 }
 
+// exp(x) for x <= 0 (the only range the Matern kernels need), ~1 ulp: round-to-nearest range
+// reduction with a two-part ln2, degree-13 Taylor polynomial on |r| <= ln2/2 (remainder 5e-18),
+// exponent patched in with an integer add.  21 FP64-pipe instructions instead of the ~46 of the
+// general-purpose library exp() that profiles/r01a showed dominating the build and gradient kernels.
+// Results below 2^-1000 are flushed to zero (they are < 1e-301 of the prior variance).
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(x, 1.4426950408889634, MAGIC);
+    const double kd = t - MAGIC;
+    const long long k = (long long)(int)(__double_as_longlong(t) & 0xffffffffLL);
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                       // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                     // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                    // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                    // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                   // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                     // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                    // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                    // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                    // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                   // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                   // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = __longlong_as_double(__double_as_longlong(p) + (k << 52));
+    return (x > -693.0) ? v : 0.0;                            // NaN input -> 0 never reached: callers pass finite r
+}
+
 // Matern-5/2 pieces from the squared scaled distance.
 __device__ __forceinline__ void matern52(double r2, double& m, double& gfac) {
     const double r = sqrt(5.0 * r2);
-    const double e = exp(-r);
+    const double e = exp_nonpos(-r);
     m = (1.0 + r + (5.0 / 3.0) * r2) * e;
     gfac = (5.0 / 6.0) * (1.0 + r) * e;      // -dm/dr2
+}
+__device__ __forceinline__ double matern52_value(double r2) {
+    const double r = sqrt(5.0 * r2);
+    return (1.0 + r + (5.0 / 3.0) * r2) * exp_nonpos(-r);
 }
 
 // Scaled coordinates in shared memory, structure-of-arrays: zs[k * Np + i] = x_ik / sqrt(M_k),
@@ -73,17 +107,13 @@ __device__ __forceinline__ double kern_value(const Coords& c, const Hyper& h, in
         const double dz = c.zs[k * c.Np + i] - c.zs[k * c.Np + j];
         r2 = fma(dz, dz, r2);
     }
-    double m, gf;
-    matern52(r2, m, gf);
-    double v = h.amp * m;
+    double v = h.amp * matern52_value(r2);
     if (c.family == 1) v *= fma(c.us[i] * c.us[j], h.inv_g2, h.cb);
     return v;
 }
 
-// Fill tile (I, J) of the covariance matrix into `tile` (swizzled).  Padding rows/cols get the
-// identity.  For diagonal tiles the strictly-upper 8x8 blocks are zeroed (tile_potrf contract).
-// Warp w writes rows 8w..8w+7, lanes across columns (conflict-free).  No barrier inside.
-__device__ __forceinline__ void build_tile(double* tile, const Coords& c, const Hyper& h, int I, int J) {
+// Generic tile fill (any padding): warp w writes rows 8w..8w+7, lanes across columns.
+__device__ __forceinline__ void build_tile_generic(double* tile, const Coords& c, const Hyper& h, int I, int J) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int rr = 0; rr < 8; ++rr) {
@@ -107,6 +137,96 @@ __device__ __forceinline__ void build_tile(double* tile, const Coords& c, const 
     }
 }
 
+// Interior off-diagonal tile, DD Matern axes known at compile time: each lane keeps the scaled
+// coordinates of its two columns in registers, the row coordinates arrive by broadcast loads.
+template <int DD>
+__device__ __forceinline__ void build_tile_offdiag(double* tile, const Coords& c, const Hyper& h, int I, int J) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool basis = c.family == 1;
+    double zc0[DD], zc1[DD];
+#pragma unroll
+    for (int k = 0; k < DD; ++k) {
+        zc0[k] = c.zs[k * c.Np + TS * J + lane];
+        zc1[k] = c.zs[k * c.Np + TS * J + lane + 32];
+    }
+    const double uc0 = c.us[TS * J + lane] * h.inv_g2, uc1 = c.us[TS * J + lane + 32] * h.inv_g2;
+#pragma unroll 2
+    for (int rr = 0; rr < 8; ++rr) {
+        const int r = 8 * w + rr, gi = TS * I + r;
+        double r20 = 0.0, r21 = 0.0;
+#pragma unroll
+        for (int k = 0; k < DD; ++k) {
+            const double zr = c.zs[k * c.Np + gi];
+            const double d0 = zr - zc0[k], d1 = zr - zc1[k];
+            r20 = fma(d0, d0, r20);
+            r21 = fma(d1, d1, r21);
+        }
+        double v0 = h.amp * matern52_value(r20), v1 = h.amp * matern52_value(r21);
+        if (basis) {
+            const double ur = c.us[gi];
+            v0 *= fma(ur, uc0, h.cb);
+            v1 *= fma(ur, uc1, h.cb);
+        }
+        tile[tix(r, lane)] = v0;
+        tile[tix(r, lane + 32)] = v1;
+    }
+}
+
+// Interior diagonal tile: only the 36 lower 8x8 blocks are evaluated (one block per warp pass,
+// two adjacent columns per lane, 16-byte stores); the 28 strictly-upper blocks are zero-filled
+// (tile_potrf contract).
+template <int DD>
+__device__ __forceinline__ void build_tile_diag(double* tile, const Coords& c, const Hyper& h, int K) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, cp = (lane & 3) * 2;
+    const bool basis = c.family == 1;
+    for (int q = w; q < 64; q += NWARPS) {
+        const int bi = q >> 3, bj = q & 7;
+        double2 v; v.x = 0.0; v.y = 0.0;
+        if (bj <= bi) {
+            const int gi = TS * K + 8 * bi + r, gj = TS * K + 8 * bj + cp;
+            double r20 = 0.0, r21 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DD; ++k) {
+                const double zr = c.zs[k * c.Np + gi];
+                const double2 zc = *reinterpret_cast<const double2*>(&c.zs[k * c.Np + gj]);
+                const double d0 = zr - zc.x, d1 = zr - zc.y;
+                r20 = fma(d0, d0, r20);
+                r21 = fma(d1, d1, r21);
+            }
+            v.x = h.amp * matern52_value(r20);
+            v.y = h.amp * matern52_value(r21);
+            if (basis) {
+                const double ur = c.us[gi] * h.inv_g2;
+                const double2 uc = *reinterpret_cast<const double2*>(&c.us[gj]);
+                v.x *= fma(ur, uc.x, h.cb);
+                v.y *= fma(ur, uc.y, h.cb);
+            }
+            if (gi == gj) v.x += h.diag_add;
+            if (gi == gj + 1) v.y += h.diag_add;
+        }
+        *reinterpret_cast<double2*>(&tile[tix(8 * bi + r, 8 * bj + cp)]) = v;
+    }
+}
+
+// Fill tile (I, J) of the covariance matrix into `tile` (swizzled).  Padding rows/cols get the
+// identity.  For diagonal tiles the strictly-upper 8x8 blocks are zeroed.  No barrier inside.
+__device__ __forceinline__ void build_tile(double* tile, const Coords& c, const Hyper& h, int I, int J) {
+    const bool interior = TS * I + TS <= c.N && TS * J + TS <= c.N;
+    if (!interior) { build_tile_generic(tile, c, h, I, J); return; }
+#define FAB_BUILD_CASE(DD)                                                    \
+    case DD:                                                                  \
+        if (I == J) build_tile_diag<DD>(tile, c, h, I);                       \
+        else build_tile_offdiag<DD>(tile, c, h, I, J);                        \
+        break;
+    switch (c.d) {
+        FAB_BUILD_CASE(1) FAB_BUILD_CASE(2) FAB_BUILD_CASE(3) FAB_BUILD_CASE(4)
+        FAB_BUILD_CASE(5) FAB_BUILD_CASE(6) FAB_BUILD_CASE(7) FAB_BUILD_CASE(8)
+        default: build_tile_generic(tile, c, h, I, J);
+    }
+#undef FAB_BUILD_CASE
+}
+
 // ---------------------------------------------------------------------------------------------
 // Shared-memory tile cache.  Every thread keeps an identical copy of the (tiny) directory in
 // registers and runs the same deterministic policy, so no communication is needed to agree on
@@ -117,18 +237,24 @@ __device__ __forceinline__ int id_row(int id) { return (id >> 16) & 0x3fff; }
 __device__ __forceinline__ int id_col(int id) { return id & 0xffff; }
 __device__ __forceinline__ int id_kind(int id) { return (id >> 30) & 1; }
 
+__device__ __forceinline__ unsigned pin(int s) { return s >= 0 ? (1u << s) : 0u; }
+
 struct TileCache {
     int id[MAX_SLOTS];
     int stamp[MAX_SLOTS];
     int nslot, clock;
-    unsigned phase;                 // mbarrier phase counter (uniform)
+    unsigned inflight;              // slots with a bulk load in flight (bit mask, uniform)
+    unsigned phases;                // per-slot mbarrier phase parity (bit mask, uniform)
     double* base;                   // nslot * TILE_ELEMS doubles of shared memory
-    unsigned long long* bar;
+    unsigned long long* bars;       // MAX_SLOTS mbarriers, one per slot
 
+    // `mb` must point to MAX_SLOTS mbarriers; thread 0 initialises them (caller syncs afterwards).
     __device__ __forceinline__ void init(double* b, int n, unsigned long long* mb) {
-        base = b; nslot = n; bar = mb; clock = 0; phase = 0;
+        base = b; nslot = n; bars = mb; clock = 0; inflight = 0u; phases = 0u;
 #pragma unroll
         for (int s = 0; s < MAX_SLOTS; ++s) { id[s] = -1; stamp[s] = 0; }
+        if (threadIdx.x == 0)
+            for (int s = 0; s < MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
     }
     __device__ __forceinline__ double* ptr(int s) const { return base + (size_t)s * TILE_ELEMS; }
     __device__ __forceinline__ void touch(int s) {
@@ -144,13 +270,13 @@ struct TileCache {
         return f;
     }
     // Pick a slot to (re)use: free first, then dead (per the caller's predicate), then least
-    // recently used; slots p0/p1/p2 are pinned.
+    // recently used; slots whose bit is set in `pins` are never chosen.
     template <typename Dead>
-    __device__ __forceinline__ int victim(Dead dead, int p0, int p1, int p2) {
+    __device__ __forceinline__ int victim(Dead dead, unsigned pins) {
         int best = -1, best_score = 0x7fffffff;
 #pragma unroll
         for (int s = 0; s < MAX_SLOTS; ++s) {
-            if (s >= nslot || s == p0 || s == p1 || s == p2) continue;
+            if (s >= nslot || ((pins >> s) & 1u)) continue;
             int score;
             if (id[s] < 0) score = -2000000000;
             else if (dead(id[s])) score = -1000000000 + stamp[s];
@@ -167,27 +293,47 @@ struct TileCache {
     // Reserve a slot for a tile that is about to be produced in shared memory.  Contains a block
     // barrier (orders earlier readers of the victim and drains its pending bulk store).
     template <typename Dead>
-    __device__ __forceinline__ int alloc(int tid_, Dead dead, int p0, int p1, int p2) {
-        const int s = victim(dead, p0, p1, p2);
+    __device__ __forceinline__ int alloc(int tid_, Dead dead, unsigned pins) {
+        const int s = victim(dead, pins | inflight);
         if (threadIdx.x == 0) bulk_s2g_wait_read();
         __syncthreads();
         set(s, tid_);
         return s;
     }
-    // Make a tile resident, loading it from the HBM/L2 workspace on a miss (TMA bulk copy).
+    // Start making a tile resident: on a miss a TMA bulk copy from the HBM/L2 workspace is issued
+    // into a victim slot and completes on that slot's mbarrier.  The caller guarantees (block
+    // barrier) that no thread still reads any unpinned slot.  No barrier inside.
     template <typename Dead>
-    __device__ __forceinline__ int acquire(const double* Lw_walker, int tid_, Dead dead, int p0, int p1, int p2) {
+    __device__ __forceinline__ int issue(const double* Lw_walker, int tid_, Dead dead, unsigned pins) {
         int s = find(tid_);
         if (s >= 0) return s;
-        s = victim(dead, p0, p1, p2);
-        __syncthreads();                       // nobody may still be reading the victim
+        s = victim(dead, pins | inflight);
         if (threadIdx.x == 0) {
             bulk_s2g_wait_all();               // write-through stores must have landed
-            bulk_g2s(ptr(s), Lw_walker + (size_t)tri_index(id_row(tid_), id_col(tid_)) * TILE_ELEMS, TILE_BYTES, bar);
+            bulk_g2s(ptr(s), Lw_walker + (size_t)tri_index(id_row(tid_), id_col(tid_)) * TILE_ELEMS, TILE_BYTES,
+                     &bars[s]);
         }
-        mbar_wait(bar, phase & 1u);
-        ++phase;
+        inflight |= 1u << s;
         set(s, tid_);
+        return s;
+    }
+    // Block until the bulk load into slot s (if any) has landed.
+    __device__ __forceinline__ void wait(int s) {
+        if ((inflight >> s) & 1u) {
+            mbar_wait(&bars[s], (phases >> s) & 1u);
+            phases ^= 1u << s;
+            inflight &= ~(1u << s);
+        }
+    }
+    // Synchronous convenience: make a tile resident now (a block barrier on a miss).
+    template <typename Dead>
+    __device__ __forceinline__ int acquire(const double* Lw_walker, int tid_, Dead dead, unsigned pins) {
+        int s = find(tid_);
+        if (s < 0) {
+            __syncthreads();                   // nobody may still be reading the victim
+            s = issue(Lw_walker, tid_, dead, pins);
+        }
+        wait(s);
         return s;
     }
 };

@@ -27,7 +27,7 @@ struct FactorArgs {
 };
 
 __host__ __device__ inline size_t factor_smem_bytes(int nslot, int Np, int d) {
-    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + (d + 5) * Np + 64) + 64;
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + (d + 5) * Np + 64) + 8 * MAX_SLOTS + 64;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
     double* diagv = accv + Np;
     double* red = diagv + Np;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 64);
-    int* fail = reinterpret_cast<int*>(bar + 1);
+    int* fail = reinterpret_cast<int*>(bar + MAX_SLOTS);
 
     const Hyper h = decode_hyper(gd, a.theta + (size_t)b * gd.Pk, a.yerr2[b]);
 
@@ -69,20 +69,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
         zv[i] = 0.0;
         diagv[i] = 1.0;
     }
-    if (tid == 0) { mbar_init(bar, 1); *fail = 0; }
-    __syncthreads();
+    if (tid == 0) *fail = 0;
 
     Coords co; co.zs = zs; co.us = us; co.Np = Np; co.N = N; co.d = d; co.family = gd.family;
     TileCache tc; tc.init(slots, a.nslot, bar);
+    __syncthreads();
     double* Lw = a.wk.Lw ? a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS : nullptr;
     double* Dw = a.wk.Dinv ? a.wk.Dinv + (size_t)b * NT * 512 : nullptr;
     const WarpTile wt = warp_tile();
     int first_fail = 0;
 
+    double* rinv = red + 32;                 // 8 reciprocal pivots of the block being factored
+    constexpr int GB = 3;                    // panel tiles solved together (ILP across their strips)
+
     for (int K = 0; K < NT; ++K) {
-        // ================= diagonal tile (K, K) =================
         auto dead = [K](int id) { return id_row(id) < K; };   // rows above the current block column are done
-        const int sd = tc.alloc(tile_id(0, K, K), dead, -1, -1, -1);
+        // ================= diagonal tile (K, K) =================
+        const int sd = tc.alloc(tile_id(0, K, K), dead, 0u);
         double* Td = tc.ptr(sd);
         build_tile(Td, co, h, K, K);
         __syncthreads();
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             double acc[4][2][2];
             acc_load(acc, Td, wt);
             for (int J = 0; J < K; ++J) {
-                const int sj = tc.acquire(Lw, tile_id(0, K, J), dead, sd, -1, -1);
+                const int sj = tc.acquire(Lw, tile_id(0, K, J), dead, pin(sd));
                 const double* Lj = tc.ptr(sj);
                 tile_mma<false, true, true>(acc, Lj, Lj, wt, 0, TS);
             }
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                 if (p == 0) zl[row] = zz;
                 __syncwarp();
             };
-            tile_potrf(Td, dinv, fail, hook);
+            tile_potrf(Td, dinv, rinv, fail, hook);
         }
         if (*fail && first_fail == 0) first_fail = TS * K + *fail;
         if (tid < TS) diagv[TS * K + tid] = Td[tix(tid, tid)];
@@ -130,39 +133,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             __syncthreads();
             if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(K, K) * TILE_ELEMS, Td, TILE_BYTES);
         }
-        // ================= panel tiles (I, K), I > K =================
-        for (int I = K + 1; I < NT; ++I) {
-            const int st = tc.alloc(tile_id(0, I, K), dead, sd, -1, -1);
-            double* Tt = tc.ptr(st);
-            build_tile(Tt, co, h, I, K);
-            __syncthreads();
-            if (K > 0) {
-                double acc[4][2][2];
-                acc_load(acc, Tt, wt);
-                for (int J = 0; J < K; ++J) {
-                    const int sa = tc.acquire(Lw, tile_id(0, I, J), dead, sd, st, -1);
-                    const int sb = tc.acquire(Lw, tile_id(0, K, J), dead, sd, st, sa);
-                    tile_mma<false, true, true>(acc, tc.ptr(sa), tc.ptr(sb), wt, 0, TS);
-                }
-                acc_store(acc, Tt, wt);
-                __syncthreads();
-            }
-            tile_trsm_right(Tt, Td, dinv);
-            // accv_I += L_IK z_K   (warp w: rows 8w..8w+7, lanes across columns)
-            {
-                const double z0 = zv[TS * K + lane], z1 = zv[TS * K + lane + 32];
+        // ================= panel tiles (I, K), I > K, in groups of up to GB =================
+        const int gb = max(1, min(GB, a.nslot - 3));   // diag + group + two streamed operands must fit the slots
+        for (int I0 = K + 1; I0 < NT; I0 += gb) {
+            const int ng = min(gb, NT - I0);
+            int st[GB];
+            double* Tt[GB];
+            unsigned pins = pin(sd);
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr) {
-                    const int r = 8 * w + rr;
-                    double s = Tt[tix(r, lane)] * z0 + Tt[tix(r, lane + 32)] * z1;
-                    s = warp_sum(s);
-                    if (lane == 0) accv[TS * I + r] += s;
+            for (int q = 0; q < GB; ++q) {
+                st[q] = -1; Tt[q] = nullptr;
+                if (q < ng) {
+                    const int I = I0 + q;
+                    st[q] = tc.alloc(tile_id(0, I, K), dead, pins);
+                    pins |= pin(st[q]);
+                    Tt[q] = tc.ptr(st[q]);
+                    build_tile(Tt[q], co, h, I, K);
+                    __syncthreads();
+                    if (K > 0) {
+                        double acc[4][2][2];
+                        acc_load(acc, Tt[q], wt);
+                        for (int J = 0; J < K; ++J) {
+                            const int sa = tc.acquire(Lw, tile_id(0, I, J), dead, pins);
+                            const int sb = tc.acquire(Lw, tile_id(0, K, J), dead, pins | pin(sa));
+                            tile_mma<false, true, true>(acc, tc.ptr(sa), tc.ptr(sb), wt, 0, TS);
+                        }
+                        acc_store(acc, Tt[q], wt);
+                    }
+                }
+            }
+            __syncthreads();
+            tile_trsm_right_multi<GB>(Tt, ng, Td, dinv);
+            // accv_I += L_IK z_K   (warp w: rows 8w..8w+7, lanes across columns)
+            const double z0 = zv[TS * K + lane], z1 = zv[TS * K + lane + 32];
+#pragma unroll
+            for (int q = 0; q < GB; ++q) {
+                if (q < ng) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = 8 * w + rr;
+                        double s = Tt[q][tix(r, lane)] * z0 + Tt[q][tix(r, lane + 32)] * z1;
+                        s = warp_sum(s);
+                        if (lane == 0) accv[TS * (I0 + q) + r] += s;
+                    }
                 }
             }
             if (a.store) {
                 fence_proxy_async();
                 __syncthreads();
-                if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(I, K) * TILE_ELEMS, Tt, TILE_BYTES);
+                if (tid == 0)
+                    for (int q = 0; q < ng; ++q)
+                        bulk_s2g(Lw + (size_t)tri_index(I0 + q, K) * TILE_ELEMS, Tt[q], TILE_BYTES);
             }
         }
         __syncthreads();

@@ -23,7 +23,7 @@ struct GradArgs {
 };
 
 __host__ __device__ inline size_t grad_smem_bytes(int nslot, int Np, int d) {
-    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + (d + 3) * Np + 512 + 128) + 64;
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + (d + 3) * Np + 512 + 128) + 8 * MAX_SLOTS + 64;
 }
 
 // alpha_J += T^T z_I for one 64x64 tile T (rows = block I, cols = block J).  Two barriers.
@@ -49,11 +49,89 @@ __device__ __forceinline__ void tile_matvec_t(const double* T, const double* zI,
     __syncthreads();
 }
 
+// Contract one 64x64 tile of (alpha alpha^T - K^-1), held in this warp's DMMA accumulator fragment,
+// with dK/dtheta regenerated from the staged observations.  DD = number of Matern axes (compile time).
+// Diagonal tiles: only 8x8 blocks on or below the diagonal are visited (weight 2 below, 1 on it).
+// gacc: [0] log_c0, [1..DD] log_M_k, [MAX_D+1] log_gamma2, [MAX_D+2] log_cb, [MAX_PK] yerr2.
+template <int DD>
+__device__ __forceinline__ void contract_tile(const double (&acc)[4][2][2], double (&gacc)[MAX_PK + 1],
+                                              const double* zs, const double* us, const double* al, const Hyper& h,
+                                              int Np, int N, int family, int I, int J, WarpTile wt) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const bool interior = TS * I + TS <= N && TS * J + TS <= N;
+    const bool basis = family == 1;
+    double gm[DD];
+#pragma unroll
+    for (int k = 0; k < DD; ++k) gm[k] = 0.0;
+    double g0 = 0.0, gg2 = 0.0, gcb = 0.0, gtr = 0.0;
+#pragma unroll 1
+    for (int j2 = 0; j2 < 2; ++j2) {
+        const int gj0 = TS * J + wt.n0 + 8 * j2 + 2 * t;
+        const int bcol = (wt.n0 >> 3) + j2;
+        double2 zc[DD];
+#pragma unroll
+        for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zs[k * Np + gj0]);
+        const double2 uc = *reinterpret_cast<const double2*>(&us[gj0]);
+        const double2 ac = *reinterpret_cast<const double2*>(&al[gj0]);
+        double kinv[4][2];                                             // this column block's K^-1 entries (static indices)
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) kinv[i4][e] = (j2 == 0) ? acc[i4][0][e] : acc[i4][1][e];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const int gi = TS * I + wt.m0 + 8 * i4 + g;
+            const int brow = (wt.m0 >> 3) + i4;
+            if (I == J && bcol > brow) continue;                       // warp-uniform
+            const double wgt = (I != J || bcol < brow) ? 2.0 : 1.0;
+            double zr[DD];
+#pragma unroll
+            for (int k = 0; k < DD; ++k) zr[k] = zs[k * Np + gi];
+            const double ur = us[gi] * h.inv_g2, ar = al[gi];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = gj0 + e;
+                if (interior || (gi < N && gj < N)) {
+                    const double wij = wgt * (ar * (e ? ac.y : ac.x) - kinv[i4][e]);
+                    double tk[DD], r2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DD; ++k) {
+                        const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                        tk[k] = dz * dz;
+                        r2 += tk[k];
+                    }
+                    double m, gf;
+                    matern52(r2, m, gf);
+                    const double uu = ur * (e ? uc.y : uc.x);
+                    const double beta = basis ? (uu + h.cb) : 1.0;
+                    const double wa = wij * h.amp;
+                    const double wam = wa * m;
+                    g0 = fma(wam, beta, g0);
+                    const double wg = wa * beta * gf;
+#pragma unroll
+                    for (int k = 0; k < DD; ++k) gm[k] = fma(wg, tk[k], gm[k]);
+                    if (basis) {
+                        gg2 = fma(-wam, uu, gg2);
+                        gcb = fma(wam, h.cb, gcb);
+                    }
+                    if (gi == gj) gtr += wij;
+                }
+            }
+        }
+    }
+    gacc[0] += g0;
+#pragma unroll
+    for (int k = 0; k < DD; ++k) gacc[1 + k] += gm[k];
+    gacc[MAX_D + 1] += gg2;
+    gacc[MAX_D + 2] += gcb;
+    gacc[MAX_PK] += gtr;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
     FAB_DYN_SMEM(smem_raw);
     const GpData& gd = a.gd;
     const int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x;
     const int Np = gd.Np, NT = gd.NT, N = gd.N, d = gd.d, Pk = gd.Pk;
 
     double* slots = reinterpret_cast<double*>(smem_raw);
@@ -90,10 +168,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
         zv[i] = a.wk.zvec[(size_t)b * Np + i];
         al[i] = 0.0;
     }
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-
     TileCache tc; tc.init(slots, a.nslot, bar);
+    __syncthreads();
     const WarpTile wt = warp_tile();
 
     // ======================= phase 1: W = L^-1 in place, alpha = W^T z =======================
@@ -101,8 +177,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
         // W tiles of earlier columns are not needed again in this phase
         auto dead = [J](int id) { return id_kind(id) == 1 && id_col(id) < J; };
         {
-            const int sl = tc.acquire(Lw, tile_id(0, J, J), dead, -1, -1, -1);
-            const int sw = tc.alloc(tile_id(1, J, J), dead, sl, -1, -1);
+            const int sl = tc.acquire(Lw, tile_id(0, J, J), dead, 0u);
+            const int sw = tc.alloc(tile_id(1, J, J), dead, pin(sl));
             for (int e = tid; e < 512; e += NTHREADS) dinv[e] = Dw[(size_t)J * 512 + e];
             __syncthreads();
             tile_trsm_left<true, false>(tc.ptr(sw), tc.ptr(sl), dinv);
@@ -112,17 +188,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
             if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(J, J) * TILE_ELEMS, tc.ptr(sw), TILE_BYTES);
         }
         for (int I = J + 1; I < NT; ++I) {
-            const int ss = tc.alloc(tile_id(1, I, J), dead, -1, -1, -1);
+            const int ss = tc.alloc(tile_id(1, I, J), dead, 0u);
             double acc[4][2][2];
             acc_zero(acc);
             for (int k = J; k < I; ++k) {
-                const int sa = tc.acquire(Lw, tile_id(0, I, k), dead, ss, -1, -1);
-                const int sb = tc.acquire(Lw, tile_id(1, k, J), dead, ss, sa, -1);
+                const int sa = tc.acquire(Lw, tile_id(0, I, k), dead, pin(ss));
+                const int sb = tc.acquire(Lw, tile_id(1, k, J), dead, pin(ss) | pin(sa));
                 // W_JJ is lower triangular: rows k' < n contribute nothing
                 tile_mma<false, false, false>(acc, tc.ptr(sa), tc.ptr(sb), wt, (k == J) ? wt.n0 : 0, TS);
             }
             acc_store(acc, tc.ptr(ss), wt);
-            const int sl = tc.acquire(Lw, tile_id(0, I, I), dead, ss, -1, -1);
+            const int sl = tc.acquire(Lw, tile_id(0, I, I), dead, pin(ss));
             for (int e = tid; e < 512; e += NTHREADS) dinv[e] = Dw[(size_t)I * 512 + e];
             __syncthreads();
             tile_trsm_left<false, true>(tc.ptr(ss), tc.ptr(sl), dinv);
@@ -145,59 +221,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
 #pragma unroll
     for (int k = 0; k <= MAX_PK; ++k) gacc[k] = 0.0;
 
-    for (int J = 0; J < NT; ++J) {
-        auto dead = [J](int id) { return id_kind(id) == 0 || id_col(id) < J; };
-        for (int I = J; I < NT; ++I) {
-            double acc[4][2][2];
-            acc_zero(acc);
-            for (int k = I; k < NT; ++k) {
-                const int sa = tc.acquire(Lw, tile_id(1, k, I), dead, -1, -1, -1);
-                const int sb = tc.acquire(Lw, tile_id(1, k, J), dead, sa, -1, -1);
-                // W_II is lower triangular: (W_II)[k'][m] = 0 for k' < m
-                tile_mma<true, false, false>(acc, tc.ptr(sa), tc.ptr(sb), wt, (k == I) ? wt.m0 : 0, TS);
+    // Static schedule of tile products (J, I, k), k = I..NT-1 innermost; the operands of step s+1 are
+    // requested (TMA bulk copies on per-slot mbarriers) before the DMMA work of step s starts.
+    {
+        int J = 0, I = 0, k = 0;
+        auto dead0 = [](int id) { return id_kind(id) == 0; };
+        int sa = tc.issue(Lw, tile_id(1, k, I), dead0, 0u);
+        int sb = tc.issue(Lw, tile_id(1, k, J), dead0, pin(sa));
+        double acc[4][2][2];
+        acc_zero(acc);
+        bool more = true;
+        while (more) {
+            // successor of (J, I, k)
+            int nJ = J, nI = I, nk = k + 1;
+            if (nk >= NT) { nI = I + 1; nk = nI; if (nI >= NT) { nJ = J + 1; nI = nJ; nk = nJ; } }
+            const bool has_next = nJ < NT;
+            __syncthreads();                   // every warp is done with the previous step's operands
+            int na = -1, nb = -1;
+            if (has_next) {
+                auto dead = [nJ](int id) { return id_kind(id) == 0 || id_col(id) < nJ; };
+                na = tc.issue(Lw, tile_id(1, nk, nI), dead, pin(sa) | pin(sb));
+                nb = tc.issue(Lw, tile_id(1, nk, nJ), dead, pin(sa) | pin(sb) | pin(na));
             }
-            // contraction with dK over this warp's 32 x 16 fragment
-            const double wgt = (I == J) ? 1.0 : 2.0;
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-                const int gi = TS * I + wt.m0 + 8 * i4 + g;
-#pragma unroll
-                for (int j2 = 0; j2 < 2; ++j2) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int gj = TS * J + wt.n0 + 8 * j2 + 2 * t + e;
-                        if (gi < N && gj < N) {
-                            const double wij = wgt * (al[gi] * al[gj] - acc[i4][j2][e]);
-                            double r2 = 0.0;
-                            double tk[MAX_D];
-#pragma unroll
-                            for (int k = 0; k < MAX_D; ++k) {
-                                if (k < d) {
-                                    const double dz = zs[k * Np + gi] - zs[k * Np + gj];
-                                    tk[k] = dz * dz;
-                                    r2 += tk[k];
-                                } else {
-                                    tk[k] = 0.0;
-                                }
-                            }
-                            double m, gf;
-                            matern52(r2, m, gf);
-                            const double uu = us[gi] * us[gj] * h.inv_g2;
-                            const double beta = (gd.family == 1) ? (uu + h.cb) : 1.0;
-                            const double wa = wij * h.amp;
-                            gacc[0] = fma(wa * m, beta, gacc[0]);
-                            const double wg = wa * beta * gf;
-#pragma unroll
-                            for (int k = 0; k < MAX_D; ++k) gacc[1 + k] = fma(wg, tk[k], gacc[1 + k]);
-                            if (gd.family == 1) {
-                                gacc[MAX_D + 1] = fma(-wa * m, uu, gacc[MAX_D + 1]);
-                                gacc[MAX_D + 2] = fma(wa * m, h.cb, gacc[MAX_D + 2]);
-                            }
-                            if (gi == gj) gacc[MAX_PK] += wij;
-                        }
-                    }
+            tc.wait(sa);
+            tc.wait(sb);
+            // W_II is lower triangular: (W_II)[k'][m] = 0 for k' < m
+            tile_mma<true, false, false>(acc, tc.ptr(sa), tc.ptr(sb), wt, (k == I) ? wt.m0 : 0, TS);
+            if (k == NT - 1) {
+                // contraction with dK over this warp's 32 x 16 fragment
+#define FAB_CONTRACT_CASE(DD) case DD: contract_tile<DD>(acc, gacc, zs, us, al, h, Np, N, gd.family, I, J, wt); break;
+                switch (d) {
+                    FAB_CONTRACT_CASE(1) FAB_CONTRACT_CASE(2) FAB_CONTRACT_CASE(3) FAB_CONTRACT_CASE(4)
+                    FAB_CONTRACT_CASE(5) FAB_CONTRACT_CASE(6) FAB_CONTRACT_CASE(7) FAB_CONTRACT_CASE(8)
                 }
+#undef FAB_CONTRACT_CASE
+                acc_zero(acc);
             }
+            J = nJ; I = nI; k = nk; sa = na; sb = nb;
+            more = has_next;
         }
     }
     __syncthreads();

@@ -129,6 +129,15 @@ __device__ __forceinline__ void bulk_s2g_wait_all() {
 #endif
 }
 
+// Named barrier among `nthreads` (multiple of 32) threads of the CTA; id 1..15 (0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+#ifdef FAB_CUSIM
+    cusim_named_barrier(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------

@@ -117,14 +117,15 @@ __device__ __forceinline__ void tile_mma(double (&acc)[MI][NJ][2], const double*
 }
 
 // ---------------------------------------------------------------------------------------------
-// 8x8 diagonal block: Cholesky + triangular inverse, done by ONE thread entirely in registers (the
-// latency-critical chain: one rsqrt per column, no cross-thread traffic).
-// Reads the lower part of block (jb, jb) of tile A, writes L (upper part of the block zeroed) back
-// and the row-major 8x8 inverse to dinv[64].  Returns the 1-based failing column or 0.
+// 8x8 diagonal block, the latency-critical serial chain (one rsqrt per column, no cross-thread
+// traffic): Cholesky by ONE thread entirely in registers.  Reads the lower part of block (jb, jb) of
+// tile A, writes L back (upper part of the block zeroed) and the 8 reciprocal diagonal entries to
+// rinv[8].  Returns the 1-based failing column (tile-local) or 0.
+// The triangular inverse of the block is NOT on this chain: inv8_block() runs on another warp while
+// the CTA performs the sub-panel and trailing updates.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int potrf8_inv8(double* A, int jb, double* dinv) {
+__device__ __forceinline__ int potrf8(double* A, int jb, double* rinv) {
     double a[8][8];
-    double ri[8];
     const int o = 8 * jb;
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -135,39 +136,37 @@ __device__ __forceinline__ int potrf8_inv8(double* A, int jb, double* dinv) {
     for (int j = 0; j < 8; ++j) {
         const double p = a[j][j];
         if (!(p > 0.0) && fail == 0) fail = j + 1;     // catches NaN too
-        const double rinv = rsqrt(p);
-        ri[j] = rinv;
+        const double ri = rsqrt(p);
+        rinv[j] = ri;
         a[j][j] = sqrt(p);
 #pragma unroll
-        for (int i = j + 1; i < 8; ++i) a[i][j] *= rinv;
+        for (int i = j + 1; i < 8; ++i) a[i][j] *= ri;
 #pragma unroll
         for (int k = j + 1; k < 8; ++k)
 #pragma unroll
             for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
     }
-    // inverse of the lower-triangular 8x8 block, column by column
-    double x[8][8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) x[r][c] = 0.0;
-        x[c][c] = ri[c];
-#pragma unroll
-        for (int r = c + 1; r < 8; ++r) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = c; k < r; ++k) s = fma(a[r][k], x[k][c], s);
-            x[r][c] = -s * ri[r];
-        }
-    }
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            A[tix(o + r, o + c)] = a[r][c];
-            dinv[r * 8 + c] = x[r][c];
-        }
+        for (int c = 0; c < 8; ++c) A[tix(o + r, o + c)] = a[r][c];
     return fail ? o + fail : 0;
+}
+
+// Column `c` (0..7, one thread each) of the row-major 8x8 inverse of the lower-triangular block
+// (jb, jb) of A: x_c = 1/l_cc, x_r = -(sum_{k<r} l_rk x_k) / l_rr for r > c, zeros above.
+__device__ __forceinline__ void inv8_column(const double* A, int jb, const double* rinv, double* dinv, int c) {
+    double x[8];
+    const int o = 8 * jb;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < r; ++k) s = fma(A[tix(o + r, o + k)], x[k], s);
+        const double ri = rinv[r];
+        x[r] = (r < c) ? 0.0 : ((r == c) ? ri : -s * ri);
+        dinv[r * 8 + c] = x[r];
+    }
 }
 
 // One DMMA-block helper: 8x8 accumulator (c0,c1) at block (bi, bj) of a tile.
@@ -185,54 +184,81 @@ __device__ __forceinline__ void blk_store(double c0, double c1, double* C, int b
 // ---------------------------------------------------------------------------------------------
 // In-tile Cholesky of a diagonal tile (lower part valid, strictly-upper 8x8 blocks must be zero).
 // On exit A = L (lower), dinv[8][64] = inverses of the eight 8x8 diagonal blocks of L.
-// `hook(jb)` is called by all threads of warp 1 while thread 0 factors block jb+1 (used to overlap
-// the forward substitution of the right-hand side with the serial chain); hook(7) runs at the end.
-// *fail (shared int) receives the first failing 1-based column within the tile, if any.
+// Per 8-column step:
+//   (a) thread 0: potrf8 of block (jb, jb) (serial chain)   ||  warp 1: hook(jb-1)
+//   (b) one thread per row below the block: x = a L8^-T by an 8-step substitution with the
+//       reciprocal pivots (right-looking, so only mul -> fma is on each row's dependent chain)
+//       ||  thread 224: inv8_block(jb) for later consumers (panel solves, hook(jb))
+//   (c) DMMA rank-8 update of the trailing blocks inside the tile
+// `hook(jb)` (all threads of warp 1) overlaps the forward substitution of the right-hand side with
+// the serial chain; hook(7) runs at the end.  *fail (shared int) receives the first failing
+// 1-based column within the tile.  `rinv` is 8 doubles of shared scratch.
 // All 256 threads must call.  Ends with a __syncthreads().
 // ---------------------------------------------------------------------------------------------
 template <typename Hook>
-__device__ __forceinline__ void tile_potrf(double* A, double* dinv, int* fail, Hook hook) {
+__device__ __forceinline__ void tile_potrf(double* A, double* dinv, double* rinv, int* fail, Hook hook) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     for (int jb = 0; jb < 8; ++jb) {
-        // (a) serial 8x8 factor + inverse  ||  overlapped hook for the previous block
         if (threadIdx.x == 0) {
-            const int f = potrf8_inv8(A, jb, dinv + 64 * jb);
+            const int f = potrf8(A, jb, rinv);
             if (f && *fail == 0) *fail = f;
         } else if (w == 1 && jb > 0) {
             hook(jb - 1);
         }
         __syncthreads();
-        if (jb == 7) break;
-        // (b) sub-panel: blocks (ib, jb), ib > jb:  X = A_blk * inv8^T   (one warp per block)
-        for (int ib = jb + 1 + w; ib < 8; ib += NWARPS) {
-            double c0 = 0.0, c1 = 0.0;
+        if (w == 7) {
+            // 8x8 inverse for later consumers (panel solves, hook(jb)): off the critical path, it
+            // spans phases (b) and (c) of the other seven warps
+            if (lane < 8) inv8_column(A, jb, rinv, dinv + 64 * jb, lane);
+        } else {
+            // (b) rows below the diagonal block, one thread each
+            const int row = 8 * (jb + 1) + threadIdx.x;
+            if (row < TS) {
+                double x[8], l[8][8], ri[8];
 #pragma unroll
-            for (int k0 = 0; k0 < 8; k0 += 4) {
-                const double a = A[tix(8 * ib + g, 8 * jb + k0 + t)];
-                const double b = dinv[64 * jb + g * 8 + k0 + t];      // B[k][n] = inv[n][k]
-                dmma(c0, c1, a, b);
-            }
-            blk_store(c0, c1, A, ib, jb);
-        }
-        __syncthreads();
-        // (c) trailing update inside the tile: blocks (ib, kb), jb < kb <= ib
-        const int m = 7 - jb;                 // trailing block rows
-        const int nblk = m * (m + 1) / 2;
-        for (int q = w; q < nblk; q += NWARPS) {
-            // unrank q -> (ri, rk) with rk <= ri, row-major over the lower triangle
-            int ri = 0, acc_ = 0;
-            while (acc_ + ri + 1 <= q) { acc_ += ri + 1; ++ri; }
-            const int rk = q - acc_;
-            const int ib = jb + 1 + ri, kb = jb + 1 + rk;
-            double c0, c1;
-            blk_load(c0, c1, A, ib, kb);
+                for (int c = 0; c < 8; c += 2) {                  // 16-byte accesses: (c, c+1) stay adjacent under the swizzle
+                    const double2 v = *reinterpret_cast<const double2*>(&A[tix(row, 8 * jb + c)]);
+                    x[c] = v.x; x[c + 1] = v.y;
+                }
 #pragma unroll
-            for (int k0 = 0; k0 < 8; k0 += 4) {
-                const double a = -A[tix(8 * ib + g, 8 * jb + k0 + t)];
-                const double b = A[tix(8 * kb + g, 8 * jb + k0 + t)];
-                dmma(c0, c1, a, b);
+                for (int c = 0; c < 8; ++c) {
+                    ri[c] = rinv[c];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) l[c][k] = (k < c) ? A[tix(8 * jb + c, 8 * jb + k)] : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    x[k] *= ri[k];
+#pragma unroll
+                    for (int c = k + 1; c < 8; ++c) x[c] = fma(-x[k], l[c][k], x[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    double2 v; v.x = x[c]; v.y = x[c + 1];
+                    *reinterpret_cast<double2*>(&A[tix(row, 8 * jb + c)]) = v;
+                }
             }
-            blk_store(c0, c1, A, ib, kb);
+            if (jb < 7) {
+                named_bar_sync(1, NTHREADS - 32);
+                // (c) trailing update inside the tile: blocks (ib, kb), jb < kb <= ib, over 7 warps
+                const int m = 7 - jb;                 // trailing block rows
+                const int nblk = m * (m + 1) / 2;
+                for (int q = w; q < nblk; q += NWARPS - 1) {
+                    int ri_ = 0, acc_ = 0;            // unrank q -> (ri_, rk), rk <= ri_, row-major lower triangle
+                    while (acc_ + ri_ + 1 <= q) { acc_ += ri_ + 1; ++ri_; }
+                    const int rk = q - acc_;
+                    const int ib = jb + 1 + ri_, kb = jb + 1 + rk;
+                    double c0, c1;
+                    blk_load(c0, c1, A, ib, kb);
+#pragma unroll
+                    for (int k0 = 0; k0 < 8; k0 += 4) {
+                        const double a = -A[tix(8 * ib + g, 8 * jb + k0 + t)];
+                        const double b = A[tix(8 * kb + g, 8 * jb + k0 + t)];
+                        dmma(c0, c1, a, b);
+                    }
+                    blk_store(c0, c1, A, ib, kb);
+                }
+            }
         }
         __syncthreads();
     }
@@ -241,38 +267,54 @@ __device__ __forceinline__ void tile_potrf(double* A, double* dinv, int* fail, H
 }
 
 // ---------------------------------------------------------------------------------------------
-// Right solve  X * L^T = A  (L = factored diagonal tile with its 8x8 inverses), X overwrites A.
-// Each warp owns an 8-row strip, so no block barrier is needed inside; ends with __syncthreads().
+// Right solve  X * L^T = A  (L = factored diagonal tile with its 8x8 inverses) for up to NB panel
+// tiles at once; X overwrites A.  Each warp owns the same 8-row strip of every tile and interleaves
+// them, so the serial 8-step chain of one strip hides behind the others (no block barriers inside).
+// Ends with __syncthreads().
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_trsm_right(double* A, const double* __restrict__ L,
-                                                const double* __restrict__ dinv) {
+template <int NB>
+__device__ __forceinline__ void tile_trsm_right_multi(double* const (&T)[NB], int n, const double* __restrict__ L,
+                                                      const double* __restrict__ dinv) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int s = w;                                  // strip = rows 8s .. 8s+7
     for (int jb = 0; jb < 8; ++jb) {
-        double c0, c1;
-        blk_load(c0, c1, A, s, jb);
+        double c0[NB], c1[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) if (q < n) blk_load(c0[q], c1[q], T[q], s, jb);
         for (int kb = 0; kb < jb; ++kb) {
 #pragma unroll
             for (int k0 = 0; k0 < 8; k0 += 4) {
-                const double a = -A[tix(8 * s + g, 8 * kb + k0 + t)];        // X_(s,kb)
                 const double b = L[tix(8 * jb + g, 8 * kb + k0 + t)];        // (L_(jb,kb))^T
-                dmma(c0, c1, a, b);
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    if (q < n) dmma(c0[q], c1[q], -T[q][tix(8 * s + g, 8 * kb + k0 + t)], b);   // X_(s,kb)
             }
         }
         // Y = acc * inv8_jb^T : round-trip acc through the tile to turn it into an A operand
-        blk_store(c0, c1, A, s, jb);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) if (q < n) blk_store(c0[q], c1[q], T[q], s, jb);
         __syncwarp();
-        double y0 = 0.0, y1 = 0.0;
+        double y0[NB], y1[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) y0[q] = y1[q] = 0.0;
 #pragma unroll
         for (int k0 = 0; k0 < 8; k0 += 4) {
-            const double a = A[tix(8 * s + g, 8 * jb + k0 + t)];
             const double b = dinv[64 * jb + g * 8 + k0 + t];
-            dmma(y0, y1, a, b);
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+                if (q < n) dmma(y0[q], y1[q], T[q][tix(8 * s + g, 8 * jb + k0 + t)], b);
         }
-        blk_store(y0, y1, A, s, jb);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) if (q < n) blk_store(y0[q], y1[q], T[q], s, jb);
         __syncwarp();
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void tile_trsm_right(double* A, const double* __restrict__ L,
+                                                const double* __restrict__ dinv) {
+    double* const T[1] = {A};
+    tile_trsm_right_multi<1>(T, 1, L, dinv);
 }
 
 // ---------------------------------------------------------------------------------------------

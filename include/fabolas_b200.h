@@ -132,6 +132,10 @@ int fab_es_information_gain_batch(fab_ctx* ctx, const double* Xc, int M, double*
 int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta, int B, const double* Xa,
                       int Na, const double* Xb, int Nb, int D, double amp_mult, double* K, double* dK);
 
+/* Debug / test knob: cap the number of shared-memory tile slots (4..6) so that small problems
+ * exercise the L2/HBM tile-streaming path of the factor and gradient kernels.                     */
+int fab_ctx_debug_set_max_slots(fab_ctx* ctx, int n);
+
 /* Debug / test access: copy the dense lower Cholesky factor of walker b (N x N row-major, device)
  * out of the tiled workspace left by the last fab_gp_loglik_batch(grad != NULL) / factorize call. */
 int fab_gp_debug_get_factor(fab_ctx* ctx, int b, double* L_out);

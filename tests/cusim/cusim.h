@@ -278,3 +278,15 @@ static inline int __syncthreads_or(int pred) {
     CUSIM_RESTORE_TID();
     return r;
 }
+// named barrier (PTX bar.sync id, nthreads): rendezvous of exactly `count` threads of the block
+static inline void cusim_named_barrier(int id, int count) {
+    static int arrived[16];
+    static unsigned long long gen[16];
+    const unsigned long long g = gen[id];
+    ++arrived[id];
+    while (gen[id] == g) {
+        if (arrived[id] >= count) { arrived[id] = 0; ++gen[id]; break; }
+        cusim::yield();
+    }
+    CUSIM_RESTORE_TID();
+}

@@ -55,6 +55,18 @@ def test_kernel_logic_emulated(sim_engine, N, D, family, B):
     _check(sim_engine, X, y, theta, yerr2, family, grad=False)
 
 
+def test_tile_streaming_path_emulated(sim_engine):
+    """Fewer shared-memory slots than tiles: factor and gradient kernels stream tiles through TMA."""
+    X, y, theta, yerr2 = _problem(200, 4, 1, 1, seed=5)          # NT = 4 -> 10 tiles
+    try:
+        sim_engine.debug_set_max_slots(4)
+        _check(sim_engine, X, y, theta, yerr2, 1, grad=True)
+        sim_engine.debug_set_max_slots(5)
+        _check(sim_engine, X, y, theta, yerr2, 1, grad=True)
+    finally:
+        sim_engine.debug_set_max_slots(6)
+
+
 def test_not_positive_definite_is_data_emulated(sim_engine):
     X, y, theta, yerr2 = _problem(20, 2, 0, 3, seed=1)
     X[5] = X[4]                                   # duplicate observation + negative jitter => indefinite
@@ -108,6 +120,17 @@ def test_baseline_configs_gpu(gpu_engine, config):
     ll1, g1, _ = gpu_engine.loglik(w["theta"], w["yerr2"], grad=True)
     assert np.max(np.abs(ll2.cpu().numpy() - ll) / np.abs(ll)) < TOL
     assert rel_err(g2.cpu().numpy(), g1.cpu().numpy(), axis=1) < 1e-8
+
+
+@pytest.mark.gpu
+def test_tile_streaming_path_gpu(gpu_engine):
+    X, y, theta, yerr2 = _problem(256, 6, 1, 5, seed=6)
+    try:
+        for n in (4, 5):
+            gpu_engine.debug_set_max_slots(n)
+            _check(gpu_engine, X, y, theta, yerr2, 1, grad=True)
+    finally:
+        gpu_engine.debug_set_max_slots(6)
 
 
 @pytest.mark.gpu
