@@ -112,12 +112,14 @@ __device__ __forceinline__ double kern_value(const Coords& c, const Hyper& h, in
     return v;
 }
 
-// Generic tile fill (any padding): warp w writes rows 8w..8w+7, lanes across columns.
-__device__ __forceinline__ void build_tile_generic(double* tile, const Coords& c, const Hyper& h, int I, int J) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Rows [row0, row0 + nrows) of tile (I, J) by the CALLING WARP, lanes across the 64 columns (two per
+// lane, conflict-free stores).  Generic version: any padding, diagonal tiles included.
+__device__ __forceinline__ void build_rows_generic(double* tile, const Coords& c, const Hyper& h, int I, int J,
+                                                   int row0, int nrows) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (int rr = 0; rr < 8; ++rr) {
-        const int r = 8 * w + rr;
+    for (int rr = 0; rr < nrows; ++rr) {
+        const int r = row0 + rr;
         const int gi = TS * I + r;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -140,8 +142,9 @@ __device__ __forceinline__ void build_tile_generic(double* tile, const Coords& c
 // Interior off-diagonal tile, DD Matern axes known at compile time: each lane keeps the scaled
 // coordinates of its two columns in registers, the row coordinates arrive by broadcast loads.
 template <int DD>
-__device__ __forceinline__ void build_tile_offdiag(double* tile, const Coords& c, const Hyper& h, int I, int J) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void build_rows_offdiag(double* tile, const Coords& c, const Hyper& h, int I, int J,
+                                                   int row0, int nrows) {
+    const int lane = threadIdx.x & 31;
     const bool basis = c.family == 1;
     double zc0[DD], zc1[DD];
 #pragma unroll
@@ -151,8 +154,8 @@ __device__ __forceinline__ void build_tile_offdiag(double* tile, const Coords& c
     }
     const double uc0 = c.us[TS * J + lane] * h.inv_g2, uc1 = c.us[TS * J + lane + 32] * h.inv_g2;
 #pragma unroll 2
-    for (int rr = 0; rr < 8; ++rr) {
-        const int r = 8 * w + rr, gi = TS * I + r;
+    for (int rr = 0; rr < nrows; ++rr) {
+        const int r = row0 + rr, gi = TS * I + r;
         double r20 = 0.0, r21 = 0.0;
 #pragma unroll
         for (int k = 0; k < DD; ++k) {
@@ -170,6 +173,20 @@ __device__ __forceinline__ void build_tile_offdiag(double* tile, const Coords& c
         tile[tix(r, lane)] = v0;
         tile[tix(r, lane + 32)] = v1;
     }
+}
+
+// Rows of an OFF-DIAGONAL tile by the calling warp (dispatch on padding and on the number of axes).
+__device__ __forceinline__ void build_rows(double* tile, const Coords& c, const Hyper& h, int I, int J, int row0,
+                                           int nrows) {
+    const bool interior = TS * I + TS <= c.N && TS * J + TS <= c.N;
+    if (!interior || I == J) { build_rows_generic(tile, c, h, I, J, row0, nrows); return; }
+#define FAB_ROWS_CASE(DD) case DD: build_rows_offdiag<DD>(tile, c, h, I, J, row0, nrows); break;
+    switch (c.d) {
+        FAB_ROWS_CASE(1) FAB_ROWS_CASE(2) FAB_ROWS_CASE(3) FAB_ROWS_CASE(4)
+        FAB_ROWS_CASE(5) FAB_ROWS_CASE(6) FAB_ROWS_CASE(7) FAB_ROWS_CASE(8)
+        default: build_rows_generic(tile, c, h, I, J, row0, nrows);
+    }
+#undef FAB_ROWS_CASE
 }
 
 // Interior diagonal tile: only the 36 lower 8x8 blocks are evaluated (one block per warp pass,
@@ -209,20 +226,17 @@ __device__ __forceinline__ void build_tile_diag(double* tile, const Coords& c, c
     }
 }
 
-// Fill tile (I, J) of the covariance matrix into `tile` (swizzled).  Padding rows/cols get the
-// identity.  For diagonal tiles the strictly-upper 8x8 blocks are zeroed.  No barrier inside.
+// Fill tile (I, J) of the covariance matrix into `tile` (swizzled), all 8 warps.  Padding rows/cols
+// get the identity.  For diagonal tiles the strictly-upper 8x8 blocks are zeroed.  No barrier inside.
 __device__ __forceinline__ void build_tile(double* tile, const Coords& c, const Hyper& h, int I, int J) {
+    const int w = threadIdx.x >> 5;
     const bool interior = TS * I + TS <= c.N && TS * J + TS <= c.N;
-    if (!interior) { build_tile_generic(tile, c, h, I, J); return; }
-#define FAB_BUILD_CASE(DD)                                                    \
-    case DD:                                                                  \
-        if (I == J) build_tile_diag<DD>(tile, c, h, I);                       \
-        else build_tile_offdiag<DD>(tile, c, h, I, J);                        \
-        break;
+    if (I != J || !interior) { build_rows(tile, c, h, I, J, 8 * w, 8); return; }
+#define FAB_BUILD_CASE(DD) case DD: build_tile_diag<DD>(tile, c, h, I); break;
     switch (c.d) {
         FAB_BUILD_CASE(1) FAB_BUILD_CASE(2) FAB_BUILD_CASE(3) FAB_BUILD_CASE(4)
         FAB_BUILD_CASE(5) FAB_BUILD_CASE(6) FAB_BUILD_CASE(7) FAB_BUILD_CASE(8)
-        default: build_tile_generic(tile, c, h, I, J);
+        default: build_rows_generic(tile, c, h, I, J, 8 * w, 8);
     }
 #undef FAB_BUILD_CASE
 }

@@ -100,6 +100,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             acc_store(acc, Td, wt);
             __syncthreads();
         }
+        // First group of panel tiles of this column: slots reserved now, covariance entries generated
+        // by warps 2..7 in the shadow of the serial 8x8 factorisations of the diagonal tile
+        // (6 half-strips of 4 rows per 8-column step => 3 tiles per diagonal tile).
+        const int gb = max(1, min(GB, a.nslot - 3));   // diag + group + two streamed operands must fit the slots
+        const int ng0 = min(gb, NT - K - 1);
+        int st0[GB];
+        double* Tt0[GB];
+        unsigned pins0 = pin(sd);
+#pragma unroll
+        for (int q = 0; q < GB; ++q) {
+            st0[q] = -1; Tt0[q] = nullptr;
+            if (q < ng0) {
+                st0[q] = tc.alloc(tile_id(0, K + 1 + q, K), dead, pins0);
+                pins0 |= pin(st0[q]);
+                Tt0[q] = tc.ptr(st0[q]);
+            }
+        }
+        auto shadow = [&](int jb, int v) {
+            const int hs = 6 * jb + v;                 // half-strip index: tile hs / 16, rows 4 * (hs % 16) ..
+            const int q = hs >> 4;
+            if (q < ng0) {
+                double* T = (q == 0) ? Tt0[0] : ((q == 1) ? Tt0[1] : Tt0[2]);
+                build_rows(T, co, h, K + 1 + q, K, 4 * (hs & 15), 4);
+            }
+        };
         {
             const double* rhs_r = rvec + TS * K;
             const double* rhs_a = accv + TS * K;
@@ -123,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                 if (p == 0) zl[row] = zz;
                 __syncwarp();
             };
-            tile_potrf(Td, dinv, rinv, fail, hook);
+            tile_potrf(Td, dinv, rinv, fail, hook, shadow);
         }
         if (*fail && first_fail == 0) first_fail = TS * K + *fail;
         if (tid < TS) diagv[TS * K + tid] = Td[tix(tid, tid)];
@@ -134,22 +159,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(K, K) * TILE_ELEMS, Td, TILE_BYTES);
         }
         // ================= panel tiles (I, K), I > K, in groups of up to GB =================
-        const int gb = max(1, min(GB, a.nslot - 3));   // diag + group + two streamed operands must fit the slots
         for (int I0 = K + 1; I0 < NT; I0 += gb) {
             const int ng = min(gb, NT - I0);
+            const bool prebuilt = I0 == K + 1;             // the first group was generated in the shadow
             int st[GB];
             double* Tt[GB];
-            unsigned pins = pin(sd);
+            unsigned pins = prebuilt ? pins0 : pin(sd);
 #pragma unroll
             for (int q = 0; q < GB; ++q) {
                 st[q] = -1; Tt[q] = nullptr;
                 if (q < ng) {
                     const int I = I0 + q;
-                    st[q] = tc.alloc(tile_id(0, I, K), dead, pins);
-                    pins |= pin(st[q]);
-                    Tt[q] = tc.ptr(st[q]);
-                    build_tile(Tt[q], co, h, I, K);
-                    __syncthreads();
+                    if (prebuilt) {
+                        st[q] = st0[q]; Tt[q] = Tt0[q];
+                    } else {
+                        st[q] = tc.alloc(tile_id(0, I, K), dead, pins);
+                        pins |= pin(st[q]);
+                        Tt[q] = tc.ptr(st[q]);
+                        build_tile(Tt[q], co, h, I, K);
+                        __syncthreads();
+                    }
                     if (K > 0) {
                         double acc[4][2][2];
                         acc_load(acc, Tt[q], wt);

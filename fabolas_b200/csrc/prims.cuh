@@ -129,6 +129,23 @@ __device__ __forceinline__ void bulk_s2g_wait_all() {
 #endif
 }
 
+// 1/sqrt(x) for normal positive x on the latency-critical Cholesky chain: hardware seed (upper 32
+// bits, ~2^-20) + one third-order (Halley) step => relative error ~2^-59, 6 dependent FP64-pipe
+// instructions instead of the library rsqrt()'s 13.  x <= 0 or NaN must be screened by the caller.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+#ifdef FAB_CUSIM
+    return 1.0 / std::sqrt(x);
+#else
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);             // 1 - x y^2
+    double q = fma(0.375, e, 0.5);
+    q = q * e;                                    // e/2 + 3 e^2/8
+    return fma(y, q, y);
+#endif
+}
+
 // Named barrier among `nthreads` (multiple of 32) threads of the CTA; id 1..15 (0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 #ifdef FAB_CUSIM

@@ -128,17 +128,25 @@ __device__ __forceinline__ int potrf8(double* A, int jb, double* rinv) {
     double a[8][8];
     const int o = 8 * jb;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 8; ++r) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) a[r][c] = (c <= r) ? A[tix(o + r, o + c)] : 0.0;
+        for (int c = 0; c < 8; c += 2) {              // 16-byte loads; (c, c+1) are adjacent under the swizzle
+            if (c <= r) {
+                const double2 v = *reinterpret_cast<const double2*>(&A[tix(o + r, o + c)]);
+                a[r][c] = v.x; a[r][c + 1] = v.y;
+            } else {
+                a[r][c] = 0.0; a[r][c + 1] = 0.0;
+            }
+        }
+    }
     int fail = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const double p = a[j][j];
         if (!(p > 0.0) && fail == 0) fail = j + 1;     // catches NaN too
-        const double ri = rsqrt(p);
+        const double ri = rsqrt_fast(p);
         rinv[j] = ri;
-        a[j][j] = sqrt(p);
+        a[j][j] = p * ri;                              // sqrt(p) without a second serial chain (<= 1.5 ulp)
 #pragma unroll
         for (int i = j + 1; i < 8; ++i) a[i][j] *= ri;
 #pragma unroll
@@ -149,7 +157,10 @@ __device__ __forceinline__ int potrf8(double* A, int jb, double* rinv) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) A[tix(o + r, o + c)] = a[r][c];
+        for (int c = 0; c < 8; c += 2) {
+            double2 v; v.x = (c <= r) ? a[r][c] : 0.0; v.y = (c + 1 <= r) ? a[r][c + 1] : 0.0;
+            *reinterpret_cast<double2*>(&A[tix(o + r, o + c)]) = v;
+        }
     return fail ? o + fail : 0;
 }
 
@@ -191,19 +202,22 @@ __device__ __forceinline__ void blk_store(double c0, double c1, double* C, int b
 //       ||  thread 224: inv8_block(jb) for later consumers (panel solves, hook(jb))
 //   (c) DMMA rank-8 update of the trailing blocks inside the tile
 // `hook(jb)` (all threads of warp 1) overlaps the forward substitution of the right-hand side with
-// the serial chain; hook(7) runs at the end.  *fail (shared int) receives the first failing
+// the serial chain; hook(7) runs at the end.  `shadow(jb, v)` (all threads of warp v + 2, v = 0..5)
+// runs independent work -- the covariance build of this column's panel tiles -- in the same window.  *fail (shared int) receives the first failing
 // 1-based column within the tile.  `rinv` is 8 doubles of shared scratch.
 // All 256 threads must call.  Ends with a __syncthreads().
 // ---------------------------------------------------------------------------------------------
-template <typename Hook>
-__device__ __forceinline__ void tile_potrf(double* A, double* dinv, double* rinv, int* fail, Hook hook) {
+template <typename Hook, typename Shadow>
+__device__ __forceinline__ void tile_potrf(double* A, double* dinv, double* rinv, int* fail, Hook hook, Shadow shadow) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     for (int jb = 0; jb < 8; ++jb) {
         if (threadIdx.x == 0) {
             const int f = potrf8(A, jb, rinv);
             if (f && *fail == 0) *fail = f;
-        } else if (w == 1 && jb > 0) {
-            hook(jb - 1);
+        } else if (w == 1) {
+            if (jb > 0) hook(jb - 1);
+        } else if (w >= 2) {
+            shadow(jb, w - 2);               // independent work of warps 2..7 in the shadow of the serial chain
         }
         __syncthreads();
         if (w == 7) {
