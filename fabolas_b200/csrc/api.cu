@@ -25,7 +25,7 @@ struct fab_ctx {
     double* dy = nullptr; size_t capy = 0;
     // workspaces
     GpWork wk{};
-    size_t capL = 0, capD = 0, capZ = 0, capA = 0;
+    size_t capL = 0, capD = 0, capZ = 0, capA = 0, capW = 0;
     double* dTheta = nullptr; size_t capT = 0;   // hyper-parameters of the resident models
     double* dYerr2 = nullptr; size_t capY = 0;
     int* dInfo = nullptr; size_t capI = 0;
@@ -131,7 +131,7 @@ int fab_ctx_destroy(fab_ctx* c) {
 #ifndef FAB_CUSIM
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 #endif
-    cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha);
+    cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw);
     delete c;
     return FAB_OK;
 }
@@ -199,12 +199,13 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
     const int ntiles = gd.NT * (gd.NT + 1) / 2;
     // slots: everything if it fits, else as many as shared memory allows (>= 4 needed)
     int nslot = ntiles < c->max_slots ? ntiles : c->max_slots;
-    while (nslot > 0 && factor_smem_bytes(nslot, gd.Np, gd.d) > (size_t)c->smem_optin) --nslot;
+    while (nslot > 0 && factor_smem_bytes(nslot, gd.d) > (size_t)c->smem_optin) --nslot;
     const bool fits = nslot >= ntiles;
     if (nslot < 4 && !fits) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA factor kernel");
     const bool need_ws = store || !fits;
+    int rc;
+    if ((rc = ensure(c, &c->wk.accw, &c->capW, (size_t)B * gd.Np)) != FAB_OK) return rc;
     if (need_ws) {
-        int rc;
         if ((rc = ensure(c, &c->wk.Lw, &c->capL, (size_t)B * ntiles * TILE_ELEMS)) != FAB_OK) return rc;
         if ((rc = ensure(c, &c->wk.Dinv, &c->capD, (size_t)B * gd.NT * 512)) != FAB_OK) return rc;
         if ((rc = ensure(c, &c->wk.zvec, &c->capZ, (size_t)B * gd.Np)) != FAB_OK) return rc;
@@ -215,7 +216,7 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
     if (!need_ws) { a.wk.Lw = nullptr; a.wk.Dinv = nullptr; a.wk.zvec = nullptr; }
     a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info;
     a.nslot = nslot; a.store = need_ws ? 1 : 0;
-    const size_t smem = factor_smem_bytes(nslot, gd.Np, gd.d);
+    const size_t smem = factor_smem_bytes(nslot, gd.d);
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     FAB_LAUNCH(gp_factor_kernel, B, NTHREADS, smem, c->stream, a);
     FAB_CUDA(c, cudaGetLastError());

@@ -27,7 +27,7 @@ struct GpWork {        // per-walker workspaces in HBM (L2-resident at the bench
     double* Dinv;      // B x NT x 512        inverses of the 8x8 diagonal blocks of L
     double* zvec;      // B x Np              z = L^-1 (y - mean)
     double* alpha;     // B x Np              alpha = K^-1 (y - mean)
-    double* hyp;       // B x 4 + MAX_D       decoded hyper-parameters (amp, inv_g2, cb, yerr2, scale_k..)
+    double* accw;      // B x Np              running sum_J L_IJ z_J of the forward substitution
 };
 
 struct Hyper {         // decoded hyper-parameters of one walker
@@ -93,22 +93,41 @@ __device__ __forceinline__ double matern52_value(double r2) {
     return (1.0 + r + (5.0 / 3.0) * r2) * exp_nonpos(-r);
 }
 
-// Scaled coordinates in shared memory, structure-of-arrays: zs[k * Np + i] = x_ik / sqrt(M_k),
-// k < d ; us[i] = basis column (x_id for family 1, unused otherwise).  Rows i >= N are padding.
+// Scaled coordinates of the 64 rows and the 64 columns of the covariance tile being generated,
+// staged in shared memory as structure-of-arrays slices: z[k * 64 + r] = x_rk / sqrt(M_k) (k < d)
+// followed by u[r] (basis column, family 1; zero otherwise).  Slices are O(64 (d+1)) regardless of N.
+__host__ __device__ constexpr int slice_doubles(int d) { return (d + 1) * TS; }
+
 struct Coords {
-    const double* zs;
-    const double* us;
-    int Np, N, d, family;
+    const double* zr;   // row slice
+    const double* zc;   // column slice
+    int N, d, family;
+    __device__ __forceinline__ const double* ur() const { return zr + d * TS; }
+    __device__ __forceinline__ const double* uc() const { return zc + d * TS; }
 };
 
-__device__ __forceinline__ double kern_value(const Coords& c, const Hyper& h, int i, int j) {
+// Stage the slice of tile-row `I` (observations 64 I .. 64 I + 63) into `buf`; all threads, no barrier.
+__device__ __forceinline__ void stage_slice(double* buf, const GpData& gd, const Hyper& h, int I) {
+    const int D = gd.D, d = gd.d;
+    for (int e = threadIdx.x; e < TS * D; e += NTHREADS) {
+        const int r = e / D, k = e - r * D;
+        const int gi = TS * I + r;
+        const double x = (gi < gd.N) ? __ldg(&gd.X[(size_t)gi * D + k]) : 0.0;
+        if (k < d) buf[k * TS + r] = x * h.scale[k];
+        else buf[d * TS + r] = x;                       // k == d only happens for family 1 (D = d + 1)
+    }
+    if (gd.family != 1)
+        for (int r = threadIdx.x; r < TS; r += NTHREADS) buf[d * TS + r] = 0.0;
+}
+
+__device__ __forceinline__ double kern_value(const Coords& c, const Hyper& h, int r, int cc) {
     double r2 = 0.0;
     for (int k = 0; k < c.d; ++k) {
-        const double dz = c.zs[k * c.Np + i] - c.zs[k * c.Np + j];
+        const double dz = c.zr[k * TS + r] - c.zc[k * TS + cc];
         r2 = fma(dz, dz, r2);
     }
     double v = h.amp * matern52_value(r2);
-    if (c.family == 1) v *= fma(c.us[i] * c.us[j], h.inv_g2, h.cb);
+    if (c.family == 1) v *= fma(c.ur()[r] * c.uc()[cc], h.inv_g2, h.cb);
     return v;
 }
 
@@ -131,7 +150,7 @@ __device__ __forceinline__ void build_rows_generic(double* tile, const Coords& c
             } else if (gi >= c.N || gj >= c.N) {
                 v = (gi == gj) ? 1.0 : 0.0;
             } else {
-                v = kern_value(c, h, gi, gj);
+                v = kern_value(c, h, r, cc);
                 if (gi == gj) v += h.diag_add;
             }
             tile[tix(r, cc)] = v;
@@ -142,31 +161,30 @@ __device__ __forceinline__ void build_rows_generic(double* tile, const Coords& c
 // Interior off-diagonal tile, DD Matern axes known at compile time: each lane keeps the scaled
 // coordinates of its two columns in registers, the row coordinates arrive by broadcast loads.
 template <int DD>
-__device__ __forceinline__ void build_rows_offdiag(double* tile, const Coords& c, const Hyper& h, int I, int J,
-                                                   int row0, int nrows) {
+__device__ __forceinline__ void build_rows_offdiag(double* tile, const Coords& c, const Hyper& h, int row0, int nrows) {
     const int lane = threadIdx.x & 31;
     const bool basis = c.family == 1;
     double zc0[DD], zc1[DD];
 #pragma unroll
     for (int k = 0; k < DD; ++k) {
-        zc0[k] = c.zs[k * c.Np + TS * J + lane];
-        zc1[k] = c.zs[k * c.Np + TS * J + lane + 32];
+        zc0[k] = c.zc[k * TS + lane];
+        zc1[k] = c.zc[k * TS + lane + 32];
     }
-    const double uc0 = c.us[TS * J + lane] * h.inv_g2, uc1 = c.us[TS * J + lane + 32] * h.inv_g2;
+    const double uc0 = c.uc()[lane] * h.inv_g2, uc1 = c.uc()[lane + 32] * h.inv_g2;
 #pragma unroll 2
     for (int rr = 0; rr < nrows; ++rr) {
-        const int r = row0 + rr, gi = TS * I + r;
+        const int r = row0 + rr;
         double r20 = 0.0, r21 = 0.0;
 #pragma unroll
         for (int k = 0; k < DD; ++k) {
-            const double zr = c.zs[k * c.Np + gi];
+            const double zr = c.zr[k * TS + r];
             const double d0 = zr - zc0[k], d1 = zr - zc1[k];
             r20 = fma(d0, d0, r20);
             r21 = fma(d1, d1, r21);
         }
         double v0 = h.amp * matern52_value(r20), v1 = h.amp * matern52_value(r21);
         if (basis) {
-            const double ur = c.us[gi];
+            const double ur = c.ur()[r];
             v0 *= fma(ur, uc0, h.cb);
             v1 *= fma(ur, uc1, h.cb);
         }
@@ -175,12 +193,12 @@ __device__ __forceinline__ void build_rows_offdiag(double* tile, const Coords& c
     }
 }
 
-// Rows of an OFF-DIAGONAL tile by the calling warp (dispatch on padding and on the number of axes).
+// Rows of a tile by the calling warp (dispatch on padding and on the number of axes).
 __device__ __forceinline__ void build_rows(double* tile, const Coords& c, const Hyper& h, int I, int J, int row0,
                                            int nrows) {
     const bool interior = TS * I + TS <= c.N && TS * J + TS <= c.N;
     if (!interior || I == J) { build_rows_generic(tile, c, h, I, J, row0, nrows); return; }
-#define FAB_ROWS_CASE(DD) case DD: build_rows_offdiag<DD>(tile, c, h, I, J, row0, nrows); break;
+#define FAB_ROWS_CASE(DD) case DD: build_rows_offdiag<DD>(tile, c, h, row0, nrows); break;
     switch (c.d) {
         FAB_ROWS_CASE(1) FAB_ROWS_CASE(2) FAB_ROWS_CASE(3) FAB_ROWS_CASE(4)
         FAB_ROWS_CASE(5) FAB_ROWS_CASE(6) FAB_ROWS_CASE(7) FAB_ROWS_CASE(8)
@@ -191,9 +209,9 @@ __device__ __forceinline__ void build_rows(double* tile, const Coords& c, const 
 
 // Interior diagonal tile: only the 36 lower 8x8 blocks are evaluated (one block per warp pass,
 // two adjacent columns per lane, 16-byte stores); the 28 strictly-upper blocks are zero-filled
-// (tile_potrf contract).
+// (tile_potrf contract).  Row and column slices coincide.
 template <int DD>
-__device__ __forceinline__ void build_tile_diag(double* tile, const Coords& c, const Hyper& h, int K) {
+__device__ __forceinline__ void build_tile_diag(double* tile, const Coords& c, const Hyper& h) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, cp = (lane & 3) * 2;
     const bool basis = c.family == 1;
@@ -201,12 +219,12 @@ __device__ __forceinline__ void build_tile_diag(double* tile, const Coords& c, c
         const int bi = q >> 3, bj = q & 7;
         double2 v; v.x = 0.0; v.y = 0.0;
         if (bj <= bi) {
-            const int gi = TS * K + 8 * bi + r, gj = TS * K + 8 * bj + cp;
+            const int li = 8 * bi + r, lj = 8 * bj + cp;
             double r20 = 0.0, r21 = 0.0;
 #pragma unroll
             for (int k = 0; k < DD; ++k) {
-                const double zr = c.zs[k * c.Np + gi];
-                const double2 zc = *reinterpret_cast<const double2*>(&c.zs[k * c.Np + gj]);
+                const double zr = c.zr[k * TS + li];
+                const double2 zc = *reinterpret_cast<const double2*>(&c.zc[k * TS + lj]);
                 const double d0 = zr - zc.x, d1 = zr - zc.y;
                 r20 = fma(d0, d0, r20);
                 r21 = fma(d1, d1, r21);
@@ -214,13 +232,13 @@ __device__ __forceinline__ void build_tile_diag(double* tile, const Coords& c, c
             v.x = h.amp * matern52_value(r20);
             v.y = h.amp * matern52_value(r21);
             if (basis) {
-                const double ur = c.us[gi] * h.inv_g2;
-                const double2 uc = *reinterpret_cast<const double2*>(&c.us[gj]);
+                const double ur = c.ur()[li] * h.inv_g2;
+                const double2 uc = *reinterpret_cast<const double2*>(&c.uc()[lj]);
                 v.x *= fma(ur, uc.x, h.cb);
                 v.y *= fma(ur, uc.y, h.cb);
             }
-            if (gi == gj) v.x += h.diag_add;
-            if (gi == gj + 1) v.y += h.diag_add;
+            if (li == lj) v.x += h.diag_add;
+            if (li == lj + 1) v.y += h.diag_add;
         }
         *reinterpret_cast<double2*>(&tile[tix(8 * bi + r, 8 * bj + cp)]) = v;
     }
@@ -232,7 +250,7 @@ __device__ __forceinline__ void build_tile(double* tile, const Coords& c, const 
     const int w = threadIdx.x >> 5;
     const bool interior = TS * I + TS <= c.N && TS * J + TS <= c.N;
     if (I != J || !interior) { build_rows(tile, c, h, I, J, 8 * w, 8); return; }
-#define FAB_BUILD_CASE(DD) case DD: build_tile_diag<DD>(tile, c, h, I); break;
+#define FAB_BUILD_CASE(DD) case DD: build_tile_diag<DD>(tile, c, h); break;
     switch (c.d) {
         FAB_BUILD_CASE(1) FAB_BUILD_CASE(2) FAB_BUILD_CASE(3) FAB_BUILD_CASE(4)
         FAB_BUILD_CASE(5) FAB_BUILD_CASE(6) FAB_BUILD_CASE(7) FAB_BUILD_CASE(8)

@@ -134,6 +134,18 @@ def test_tile_streaming_path_gpu(gpu_engine):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [1000, 2048])
+def test_large_history_loglik_gpu(gpu_engine, N):
+    """BASELINE configs[4] shape (N = 2048 observations): the factor streams its tiles through TMA."""
+    w = gp_workload(5, n_walkers=3) if N == 2048 else None
+    if w is None:
+        X, y, theta, yerr2 = _problem(N, 6, 1, 3, seed=N)
+        _check(gpu_engine, X, y, theta, yerr2, 1, grad=False)
+    else:
+        _check(gpu_engine, w["X"], w["y"], w["theta"], w["yerr2"], w["family"], grad=False, amp_mult=w["amp_mult"])
+
+
+@pytest.mark.gpu
 def test_golden_svm_mnist_prior_gpu(gpu_engine):
     g = golden("gp_oracle_svm_mnist.npz")                      # the reference's real prior CSV (N=100, D=3)
     gpu_engine.set_data(1, g["X"], g["y"], float(g["y"].mean()), 3)
