@@ -78,7 +78,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = 2
+    per_core = 8
     pool = mp.get_context("spawn").Pool(cores)
     pool.map(_cpu_worker, [(CONFIG_ID, 0, 1)] * cores)
     for _ in range(args.warmup):
@@ -236,6 +236,48 @@ def run_ours(args):
     kt = np.array(kt)
     ms_factor, ms_grad = float(np.mean(kt[:, 0])), float(np.mean(kt[:, 1]))
 
+    # ---- second headline number: Entropy-Search acquisition evaluations per second (BASELINE configs[2]) ----
+    # Z = 50 representers, I = 20 innovations, 2048 candidates per GPU x 128 hyper-samples at N = 256.
+    # Setup (fit -> predict at representers -> EI -> EPMGP -> es_setup) is timed separately.
+    Z, I_, M = 50, 20, 2048
+    rng = np.random.default_rng(20260003 + rank)
+    lo = np.array([4, 4, 4, 32, -6, 1 / 256]); hi = np.array([9, 9, 9, 512, -1, 1.0])
+    reps = rng.uniform(lo, hi, (Bg, Z, D)); Omega = rng.standard_normal((Bg, I_, Z)); cand = rng.uniform(lo, hi, (M, D))
+    cand_d = eng.tensor(cand)
+
+    def es_setup():
+        eng.fit(theta_d, yerr2_d)
+        mu_r, _, cov_r = eng.predict(reps, want_var=True, want_cov=True)
+        cov_c = torch.clamp(cov_r, min=np.finfo(np.float64).eps)                  # fabolas.py:192
+        y_inc = mu_r.max(dim=1).values
+        ei_r, _, _ = eng.expected_improvement(mu_r, torch.diagonal(cov_c, dim1=1, dim2=2).contiguous(), y_inc)
+        U = torch.clamp(ei_r, min=np.finfo(np.float64).eps)
+        pm = eng.joint_min(mu_r, cov_c)
+        eng.es_setup(reps, cov_r, pm[:4], U, Omega)
+        return pm[4]
+    es_setup(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); ep_info = es_setup(); torch.cuda.synchronize()
+    es_setup_ms = (time.perf_counter() - t0) * 1e3
+    for _ in range(2):
+        eng.information_gain(cand_d)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n_ig = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_ig):
+        ig, flag = eng.information_gain(cand_d)
+    e1.record(); torch.cuda.synchronize()
+    t_ig = torch.tensor([e0.elapsed_time(e1) / n_ig], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ig, op=dist.ReduceOp.MAX)
+    ms_ig = float(t_ig.item())
+    es_out = {"value": world * M / (ms_ig * 1e-3), "unit": "information-gain evals/s (each: 128 hyper-samples x 20 innovations, Z=50)",
+              "candidates_per_gpu": M, "ms_per_sweep": ms_ig, "setup_ms_fit_predict_ei_epmgp": es_setup_ms,
+              "nan_flags": int(flag.sum()), "epmgp_info_max": int(ep_info.max())}
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])       # back to the ll+grad problem state
+
     # parity spot check of the timed path against the oracle (2 walkers; cheap)
     ll, g = step_resident()
     torch.cuda.synchronize()
@@ -291,6 +333,7 @@ def run_ours(args):
                          "factor_kernel": {"achieved": factor_tf, "frac": factor_tf / peak, "ms_per_launch": ms_factor,
                                            "flops_per_eval": f_ll},
                          "whole_step_frac": Bg * f_llg / (ms_step * 1e-3) / 1e12 / peak},
+            "es_acquisition": es_out,
             "cpu_baseline": None if cpu_val is None else {
                 "value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{n_evals} ll+grad evals of the same workload, one single-threaded numpy/scipy oracle "

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 using namespace fab;
 
@@ -40,6 +41,10 @@ struct fab_ctx {
     int wsB = 0;            // walkers the factor workspace currently describes
     bool factored = false;
     bool inverted = false;  // workspace holds W = L^-1 (and alpha) instead of L
+    // cached device copies of the static tile programs: [0] fit (phase 1 only), [1] gradient
+    TileOp* dProg[2] = {nullptr, nullptr};
+    int progN[2] = {0, 0}, progNT[2] = {-1, -1}, progSlots[2] = {-1, -1};
+    std::vector<TileOp> hProg[2];
     int smem_optin = 232448;
     int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
     // optional per-kernel timing (CUDA events on the launching stream)
@@ -131,7 +136,7 @@ int fab_ctx_destroy(fab_ctx* c) {
 #ifndef FAB_CUSIM
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 #endif
-    cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw);
+    cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw); cudaFree(c->dProg[0]); cudaFree(c->dProg[1]);
     delete c;
     return FAB_OK;
 }
@@ -230,14 +235,24 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
 // W = L^-1 in place + alpha (+ gradient when grad != null); needs the workspace of launch_factor(store).
 static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int B, double* grad, const int* info) {
     const GpData& gd = c->gd;
-    const int ntiles = gd.NT * (gd.NT + 1) / 2;
     int nslot = c->max_slots;
-    while (nslot > 0 && grad_smem_bytes(nslot, gd.Np, gd.d) > (size_t)c->smem_optin) --nslot;
-    if (nslot > 2 * ntiles) nslot = 2 * ntiles;
-    if (nslot < 4 && nslot < 2 * ntiles) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA gradient kernel");
+    while (nslot > 0 && grad_smem_bytes(nslot, gd.d) > (size_t)c->smem_optin) --nslot;
+    if (nslot < 3) return fail(c, FAB_EUNSUPPORTED, "not enough shared memory for the gradient kernel");
+    const int which = grad ? 1 : 0;
+    if (c->progNT[which] != gd.NT || c->progSlots[which] != nslot) {
+        c->hProg[which] = build_grad_program(gd.NT, nslot, grad != nullptr);   // host vector stays alive: async copy source
+        const size_t n = c->hProg[which].size();
+        if (c->dProg[which]) { cudaFree(c->dProg[which]); c->dProg[which] = nullptr; }
+        if (cudaMalloc(reinterpret_cast<void**>(&c->dProg[which]), n * sizeof(TileOp)) != cudaSuccess)
+            return fail(c, FAB_ENOMEM, "tile program allocation failed");
+        FAB_CUDA(c, cudaMemcpyAsync(c->dProg[which], c->hProg[which].data(), n * sizeof(TileOp), cudaMemcpyHostToDevice,
+                                    c->stream));
+        c->progN[which] = (int)n; c->progNT[which] = gd.NT; c->progSlots[which] = nslot;
+    }
     GradArgs a;
     a.gd = gd; a.wk = c->wk; a.theta = theta; a.yerr2 = yerr2; a.grad = grad; a.info = info; a.nslot = nslot;
-    FAB_LAUNCH(gp_grad_kernel, B, NTHREADS, grad_smem_bytes(nslot, gd.Np, gd.d), c->stream, a);
+    a.prog = c->dProg[which]; a.nops = c->progN[which];
+    FAB_LAUNCH(gp_grad_kernel, B, NTHREADS, grad_smem_bytes(nslot, gd.d), c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[2], c->stream)); c->ev_used = 2; }
     c->inverted = true;
