@@ -45,6 +45,7 @@ SIGNATURES = {
     "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
     "fab_ctx_debug_set_max_slots": (_c_int, [_vp, _c_int]),
+    "fab_ctx_debug_force_slices": (_c_int, [_vp, _c_int]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
 }
 
@@ -132,6 +133,9 @@ class Engine:
 
     def debug_set_max_slots(self, n: int):
         self._check(self.lib.fab_ctx_debug_set_max_slots(self._ctx, n), "fab_ctx_debug_set_max_slots")
+
+    def debug_force_slices(self, on: bool):
+        self._check(self.lib.fab_ctx_debug_force_slices(self._ctx, int(on)), "fab_ctx_debug_force_slices")
 
     def get_timing(self):
         """Durations (ms) of the kernels launched by the most recent batched call."""

@@ -47,6 +47,7 @@ struct fab_ctx {
     std::vector<TileOp> hProg[2];
     int smem_optin = 232448;
     int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
+    int force_slices = 0;        // test knob: never keep all coordinates resident in the gradient kernel
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -147,6 +148,12 @@ int fab_ctx_debug_set_max_slots(fab_ctx* c, int n) {
     return FAB_OK;
 }
 
+int fab_ctx_debug_force_slices(fab_ctx* c, int on) {
+    if (!c) return FAB_EINVAL;
+    c->force_slices = on != 0;
+    return FAB_OK;
+}
+
 int fab_ctx_set_timing(fab_ctx* c, int enable) {
     if (!c) return FAB_EINVAL;
 #ifndef FAB_CUSIM
@@ -236,7 +243,9 @@ static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, i
 static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int B, double* grad, const int* info) {
     const GpData& gd = c->gd;
     int nslot = c->max_slots;
-    while (nslot > 0 && grad_smem_bytes(nslot, gd.d) > (size_t)c->smem_optin) --nslot;
+    // coordinates + alpha of all rows resident in shared memory when that costs no tile slot
+    int resident = (!c->force_slices && grad_smem_bytes(nslot, gd.d, gd.Np) <= (size_t)c->smem_optin) ? 1 : 0;
+    while (nslot > 0 && grad_smem_bytes(nslot, gd.d, resident ? gd.Np : 0) > (size_t)c->smem_optin) --nslot;
     if (nslot < 3) return fail(c, FAB_EUNSUPPORTED, "not enough shared memory for the gradient kernel");
     const int which = grad ? 1 : 0;
     if (c->progNT[which] != gd.NT || c->progSlots[which] != nslot) {
@@ -251,8 +260,8 @@ static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int
     }
     GradArgs a;
     a.gd = gd; a.wk = c->wk; a.theta = theta; a.yerr2 = yerr2; a.grad = grad; a.info = info; a.nslot = nslot;
-    a.prog = c->dProg[which]; a.nops = c->progN[which];
-    FAB_LAUNCH(gp_grad_kernel, B, NTHREADS, grad_smem_bytes(nslot, gd.d), c->stream, a);
+    a.prog = c->dProg[which]; a.nops = c->progN[which]; a.resident = resident;
+    FAB_LAUNCH(gp_grad_kernel, B, NTHREADS, grad_smem_bytes(nslot, gd.d, resident ? gd.Np : 0), c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[2], c->stream)); c->ev_used = 2; }
     c->inverted = true;

@@ -16,6 +16,8 @@
 
 namespace fab {
 
+// Coordinates / alpha for the contraction: 64-row slices staged per (I, J) pair (any N), or -- when
+// (d + 2) * Np doubles fit next to the tile slots -- everything resident in shared memory from the start.
 struct GradArgs {
     GpData gd;
     GpWork wk;
@@ -26,10 +28,12 @@ struct GradArgs {
     const TileOp* prog;    // device copy of the tile program
     int nops;
     int nslot;
+    int resident;          // 1: coordinates and alpha of all Np rows live in shared memory
 };
 
-__host__ __device__ inline size_t grad_smem_bytes(int nslot, int d) {
-    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(2 * 512 + 2 * (d + 1) * TS + 2 * TS + 512 + 128) + 8 * (MAX_SLOTS + 2) + 64;
+__host__ __device__ inline size_t grad_smem_bytes(int nslot, int d, int resident_np) {
+    const size_t coords = resident_np ? (size_t)(d + 2) * resident_np : (size_t)(2 * (d + 1) * TS + 2 * TS);
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(2 * 512 + 512 + 128) + 8 * coords + 8 * (MAX_SLOTS + 2) + 64;
 }
 
 // alpha_J += T^T z_I for one 64x64 tile T (rows = block I, cols = block J); alpha lives in the HBM
@@ -62,14 +66,12 @@ __device__ __forceinline__ void tile_matvec_t(const double* T, const double* __r
 // gacc: [0] log_c0, [1..DD] log_M_k, [MAX_D+1] log_gamma2, [MAX_D+2] log_cb, [MAX_PK] yerr2.
 template <int DD>
 __device__ __forceinline__ void contract_tile(const double (&acc)[4][2][2], double (&gacc)[MAX_PK + 1],
-                                              const double* zr_s, const double* zc_s, const double* al_r,
-                                              const double* al_c, const Hyper& h, int N, int family, int I, int J,
-                                              WarpTile wt) {
+                                              const double* zr_s, const double* zc_s, const double* ur_s,
+                                              const double* uc_s, const double* al_r, const double* al_c, int ldz,
+                                              const Hyper& h, int N, int family, int I, int J, WarpTile wt) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const bool interior = TS * I + TS <= N && TS * J + TS <= N;
     const bool basis = family == 1;
-    const double* ur_s = zr_s + DD * TS;
-    const double* uc_s = zc_s + DD * TS;
     double gm[DD];
 #pragma unroll
     for (int k = 0; k < DD; ++k) gm[k] = 0.0;
@@ -80,7 +82,7 @@ __device__ __forceinline__ void contract_tile(const double (&acc)[4][2][2], doub
         const int bcol = (wt.n0 >> 3) + j2;
         double2 zc[DD];
 #pragma unroll
-        for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * TS + lj0]);
+        for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
         const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
         const double2 ac = *reinterpret_cast<const double2*>(&al_c[lj0]);
         double kinv[4][2];                                             // this column block's K^-1 entries (static indices)
@@ -97,7 +99,7 @@ __device__ __forceinline__ void contract_tile(const double (&acc)[4][2][2], doub
             const double wgt = (I != J || bcol < brow) ? 2.0 : 1.0;
             double zr[DD];
 #pragma unroll
-            for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * TS + li];
+            for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
             const double ur = ur_s[li] * h.inv_g2, ar = al_r[li];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -148,13 +150,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
 
     double* slots = reinterpret_cast<double*>(smem_raw);
     double* dinvb = slots + (size_t)a.nslot * TILE_ELEMS;     // 2 x 512
-    double* sl_r = dinvb + 2 * 512;                           // coordinate slice of the row tile I
-    double* sl_c = sl_r + SL;                                 // ... of the column tile J
-    double* al_r = sl_c + SL;                                 // 64: alpha of row tile
-    double* al_c = al_r + TS;                                 // 64
-    double* part = al_c + TS;                                 // 512
+    double* part = dinvb + 2 * 512;                           // 512
     double* red = part + 512;                                 // 128
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(red + 128);   // MAX_SLOTS + 2 mbarriers
+    double* cbase = red + 128;                                // coordinates: slices or resident arrays
+    double* sl_r = cbase;                                     // slice mode: coordinate slice of the row tile I
+    double* sl_c = sl_r + SL;                                 //             ... of the column tile J
+    double* al_r = sl_c + SL;                                 //             64: alpha of row tile
+    double* al_c = al_r + TS;                                 //             64
+    double* zs_all = cbase;                                   // resident mode: zs[k * Np + i], us[i], alpha[i]
+    double* us_all = zs_all + (size_t)d * Np;
+    double* al_all = us_all + Np;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+        cbase + (a.resident ? (size_t)(d + 2) * Np : (size_t)(2 * SL + 2 * TS)));   // MAX_SLOTS + 2 mbarriers
 
     const Hyper h = decode_hyper(gd, a.theta + (size_t)b * Pk, a.yerr2[b]);
     double* Lw = a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS;
@@ -167,6 +174,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
         return;
     }
     for (int i = tid; i < Np; i += NTHREADS) alg[i] = 0.0;
+    if (a.resident) {
+        for (int e = tid; e < N * gd.D; e += NTHREADS) {
+            const int i = e / gd.D, k = e - i * gd.D;
+            const double x = __ldg(&gd.X[e]);
+            if (k < d) zs_all[k * Np + i] = x * h.scale[k];
+            else us_all[i] = x;
+        }
+        for (int i = tid; i < Np; i += NTHREADS) {
+            if (i >= N) { for (int k = 0; k < d; ++k) zs_all[k * Np + i] = 0.0; }
+            if (i >= N || gd.family != 1) us_all[i] = 0.0;
+        }
+    }
     if (tid == 0)
         for (int s = 0; s < MAX_SLOTS + 2; ++s) mbar_init(&bars[s], 1);
     __syncthreads();
@@ -185,7 +204,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
         const int type = __ldg(&opp->type), I = __ldg(&opp->I), J = __ldg(&opp->J), k = __ldg(&opp->k);
         const int sA = __ldg(&opp->slotA), sB = __ldg(&opp->slotB), sC = __ldg(&opp->slotC);
         const int wait_mask = __ldg(&opp->wait_mask), dbuf = __ldg(&opp->dinv_buf), flags = __ldg(&opp->flags);
-        if (tid == 0) bulk_s2g_wait_read();     // sources of earlier bulk stores may be overwritten from here on
+        if (tid == 0 && (flags & OPF_WAIT_READ)) bulk_s2g_wait_read();   // a stored tile's slot is overwritten from here on
         __syncthreads();                        // every warp is done with the previous operation
         if (tid == 0) {
             const int nload = __ldg(&opp->nload);
@@ -227,7 +246,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
             __syncthreads();
             if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(I, J) * TILE_ELEMS, C, TILE_BYTES);
         } else {   // OP_P2_MMA
-            if (flags & OPF_NEW_PAIR) {
+            if (a.resident) {
+                if (i == 0 || (__ldg(&(opp - 1)->type) != OP_P2_MMA)) {       // first phase-2 operation: alpha is final
+                    for (int q = tid; q < Np; q += NTHREADS) al_all[q] = alg[q];
+                    __syncthreads();
+                }
+            } else if (flags & OPF_NEW_PAIR) {
                 stage_slice(sl_r, gd, h, I);
                 stage_slice(sl_c, gd, h, J);
                 if (tid < TS) al_r[tid] = alg[TS * I + tid];
@@ -237,8 +261,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
             // W_II is lower triangular: (W_II)[k'][m] = 0 for k' < m
             tile_mma<true, false, false>(acc, A, slots + (size_t)sB * TILE_ELEMS, wt, (k == I) ? wt.m0 : 0, TS);
             if (flags & OPF_LAST) {
-                if (flags & OPF_NEW_PAIR) __syncthreads();      // slices staged in this very operation
-#define FAB_CONTRACT_CASE(DD) case DD: contract_tile<DD>(acc, gacc, sl_r, sl_c, al_r, al_c, h, N, gd.family, I, J, wt); break;
+                if (!a.resident && (flags & OPF_NEW_PAIR)) __syncthreads();      // slices staged in this very operation
+                const double* zr_p = a.resident ? zs_all + TS * I : sl_r;
+                const double* zc_p = a.resident ? zs_all + TS * J : sl_c;
+                const double* ur_p = a.resident ? us_all + TS * I : sl_r + d * TS;
+                const double* uc_p = a.resident ? us_all + TS * J : sl_c + d * TS;
+                const double* ar_p = a.resident ? al_all + TS * I : al_r;
+                const double* ac_p = a.resident ? al_all + TS * J : al_c;
+                const int ldz = a.resident ? Np : TS;
+#define FAB_CONTRACT_CASE(DD) case DD: contract_tile<DD>(acc, gacc, zr_p, zc_p, ur_p, uc_p, ar_p, ac_p, ldz, h, N, gd.family, I, J, wt); break;
                 switch (d) {
                     FAB_CONTRACT_CASE(1) FAB_CONTRACT_CASE(2) FAB_CONTRACT_CASE(3) FAB_CONTRACT_CASE(4)
                     FAB_CONTRACT_CASE(5) FAB_CONTRACT_CASE(6) FAB_CONTRACT_CASE(7) FAB_CONTRACT_CASE(8)

@@ -25,7 +25,8 @@ enum TileOpFlags {
     OPF_DRAIN_STORES = 1,   // wait for all bulk stores before issuing this op's loads (RAW through HBM)
     OPF_FIRST = 2,          // first product of an accumulation: acc = 0
     OPF_LAST = 4,           // last product: contraction (phase 2)
-    OPF_NEW_PAIR = 8        // first op of a (I, J) pair in phase 2: stage coordinate / alpha slices
+    OPF_NEW_PAIR = 8,       // first op of a (I, J) pair in phase 2: stage coordinate / alpha slices
+    OPF_WAIT_READ = 16      // a slot whose tile is the source of an earlier bulk store gets overwritten here
 };
 constexpr int TP_DINV_SLOT0 = 8;      // ld_slot values >= 8 address the two 4 KB dinv buffers
 constexpr int TP_MAX_LOADS = 12;     // <= 3 loads per op, hoisted from at most 4 ops (depth 3) into one
@@ -83,7 +84,8 @@ inline std::vector<TileOp> build_grad_program(int NT, int nslot, bool with_grad)
 
     std::vector<TileOp> prog(n);
     std::vector<int> slot_id(nslot, -1), slot_last(nslot, -1);
-    struct Load { int slot, tile, needed_at, free_from; bool is_w; };
+    struct Load { int slot, tile, needed_at, free_from; bool is_w; bool after_store; };
+    std::vector<char> slot_stored(nslot, 0);          // current content was written through to HBM by a bulk store
     std::vector<Load> loads;
     int dinv_row[2] = {-1, -1}, dinv_last[2] = {-1, -1};
 
@@ -106,8 +108,9 @@ inline std::vector<TileOp> build_grad_program(int NT, int nslot, bool with_grad)
                 const int nu = slot_id[q] < 0 ? (1 << 30) + 1 : next_use(slot_id[q], i - 1);
                 if (nu > best_next) { best_next = nu; best = q; }
             }
-            loads.push_back({best, tp_tri((id >> 16) & 0x3fff, id & 0xffff), i, slot_last[best] + 1, ((id >> 30) & 1) != 0});
-            slot_id[best] = id; slot_last[best] = i;
+            loads.push_back({best, tp_tri((id >> 16) & 0x3fff, id & 0xffff), i, slot_last[best] + 1, ((id >> 30) & 1) != 0,
+                             slot_stored[best] != 0});
+            slot_id[best] = id; slot_last[best] = i; slot_stored[best] = 0;
             op.wait_mask |= 1 << best;               // the demanding op waits; later hits find the tile landed
             busy |= 1u << best;
             return best;
@@ -121,14 +124,15 @@ inline std::vector<TileOp> build_grad_program(int NT, int nslot, bool with_grad)
                 const int nu = slot_id[q] < 0 ? (1 << 30) + 1 : next_use(slot_id[q], i);
                 if (nu > best_next) { best_next = nu; best = q; }
             }
-            slot_id[best] = s.idC; slot_last[best] = i;
+            if (slot_stored[best]) op.flags |= OPF_WAIT_READ;
+            slot_id[best] = s.idC; slot_last[best] = i; slot_stored[best] = 1;   // every output is stored at the end of its op
             op.slotC = best;
         }
         if (s.dinv >= 0) {                             // 4 KB block of 8x8 inverses of L(dinv, dinv)
             int bsel = (dinv_row[0] == s.dinv) ? 0 : ((dinv_row[1] == s.dinv) ? 1 : -1);
             if (bsel < 0) {
                 bsel = dinv_last[0] <= dinv_last[1] ? 0 : 1;
-                loads.push_back({TP_DINV_SLOT0 + bsel, s.dinv, i, dinv_last[bsel] + 1, false});
+                loads.push_back({TP_DINV_SLOT0 + bsel, s.dinv, i, dinv_last[bsel] + 1, false, false});
                 dinv_row[bsel] = s.dinv;
                 op.wait_mask |= 1 << (TP_DINV_SLOT0 + bsel);
             }
@@ -146,6 +150,7 @@ inline std::vector<TileOp> build_grad_program(int NT, int nslot, bool with_grad)
         op.ld_tile[op.nload] = l.tile;
         ++op.nload;
         if (l.is_w && e < n_phase1) op.flags |= OPF_DRAIN_STORES;   // W tiles are re-read after an in-place store
+        if (l.after_store) op.flags |= OPF_WAIT_READ;
     }
     if (n > n_phase1) prog[n_phase1].flags |= OPF_DRAIN_STORES;     // phase 2 starts with every W tile landed in HBM
     return prog;

@@ -135,6 +135,9 @@ int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta
 /* Debug / test knob: cap the number of shared-memory tile slots (4..6) so that small problems
  * exercise the L2/HBM tile-streaming path of the factor and gradient kernels.                     */
 int fab_ctx_debug_set_max_slots(fab_ctx* ctx, int n);
+/* Debug / test knob: make the gradient kernel stage 64-row coordinate slices per tile pair (its
+ * large-N mode) even when all coordinates would fit in shared memory.                              */
+int fab_ctx_debug_force_slices(fab_ctx* ctx, int on);
 
 /* Debug / test access: copy the dense lower Cholesky factor of walker b (N x N row-major, device)
  * out of the tiled workspace left by the last fab_gp_loglik_batch(grad != NULL) / factorize call. */

@@ -62,9 +62,11 @@ def test_tile_streaming_path_emulated(sim_engine):
         sim_engine.debug_set_max_slots(4)
         _check(sim_engine, X, y, theta, yerr2, 1, grad=True)
         sim_engine.debug_set_max_slots(5)
+        sim_engine.debug_force_slices(True)                       # large-N mode of the gradient kernel
         _check(sim_engine, X, y, theta, yerr2, 1, grad=True)
     finally:
         sim_engine.debug_set_max_slots(6)
+        sim_engine.debug_force_slices(False)
 
 
 def test_not_positive_definite_is_data_emulated(sim_engine):
