@@ -177,22 +177,22 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
             sdm[tid] = s * (c0 * coef[6 * Z + tid] + coef[7 * Z + tid]);
         }
         __syncthreads();
+        // one (innovation p, column bb) pair per thread pass: I * Z columns over the whole CTA
         double acc = 0.0;
-        for (int p = w; p < I; p += nw) {
-            for (int bb = lane; bb < Z; bb += 32) {
-                const double o = om[p * Z + bb];
-                double mx = -INFINITY;
-                for (int q = 0; q < Z; ++q) mx = fmax(mx, fma(sdm[q], o, det[q]));
-                double se = 0.0, sw = 0.0;
-                for (int q = 0; q < Z; ++q) {
-                    const double t = fma(sdm[q], o, det[q]);
-                    const double e = exp(t - mx);
-                    se += e;
-                    sw = fma(e, t, sw);
-                }
-                const double lse = mx + log(se);
-                acc += base - (sw / se - lse + logU[bb]);
+        for (int c = tid; c < I * Z; c += ES_THREADS) {
+            const int bb = c % Z;
+            const double o = om[c];                       // om[p * Z + bb]
+            double mx = -INFINITY;
+            for (int q = 0; q < Z; ++q) mx = fmax(mx, fma(sdm[q], o, det[q]));
+            double se = 0.0, sw = 0.0;
+            for (int q = 0; q < Z; ++q) {
+                const double t = fma(sdm[q], o, det[q]);
+                const double e = exp_nonpos(t - mx);      // t <= mx; non-finite t makes the sums NaN -> nan_flag
+                se += e;
+                sw = fma(e, t, sw);
             }
+            const double lse = mx + log(se);
+            acc += base - (sw / se - lse + logU[bb]);
         }
         acc = warp_sum(acc);
         if (lane == 0) red[w] = acc;
