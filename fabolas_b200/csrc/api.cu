@@ -474,3 +474,15 @@ int fab_gp_debug_get_factor(fab_ctx* c, int b, double* L_out) {
 }
 
 }  // extern "C"
+
+#if defined(FAB_PHASE_PROF) && !defined(FAB_CUSIM)
+// Development build only (tools/phase_prof.py): per-phase cycle counters of CTA 0.
+extern "C" int fab_debug_phase_reset(void) {
+    long long z[64] = {0};
+    return cudaMemcpyToSymbol(fab::g_phase, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int fab_debug_phase_read(long long* out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, fab::g_phase, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -31,7 +31,7 @@ struct FactorArgs {
 
 __host__ __device__ inline size_t factor_smem_bytes(int nslot, int d) {
     return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + (1 + FACTOR_GB) * (d + 1) * TS + 2 * TS + 64) +
-           8 * MAX_SLOTS + 64;
+           8 * MAX_SLOTS + 64 + 8 * EXP_TAB_N;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
@@ -51,12 +51,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
     double* red = zl + TS;                       // 64 scratch
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 64);
     int* fail = reinterpret_cast<int*>(bar + MAX_SLOTS);
+    double* etab = reinterpret_cast<double*>(bar + MAX_SLOTS + 8);   // exp table of the fast Matern evaluation
     double* rinv = red + 32;                     // 8 reciprocal pivots of the block being factored
 
+    PHB(0);
     const Hyper h = decode_hyper(gd, a.theta + (size_t)b * gd.Pk, a.yerr2[b]);
     double* accw = a.wk.accw + (size_t)b * Np;
     for (int i = tid; i < Np; i += NTHREADS) accw[i] = 0.0;
     if (tid == 0) *fail = 0;
+    exp_table_fill(etab);
 
     TileCache tc; tc.init(slots, a.nslot, bar);
     __syncthreads();
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
     for (int K = 0; K < NT; ++K) {
         auto dead = [K](int id) { return id_row(id) < K; };   // rows above the current block column are done
         // ================= diagonal tile (K, K) =================
+        PHB(1);
         const int sd = tc.alloc(tile_id(0, K, K), dead, 0u);  // (block barrier inside: slices are free to overwrite)
         double* Td = tc.ptr(sd);
         stage_slice(sl_col, gd, h, K);
@@ -77,9 +81,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             rhs[tid] = (gi < N) ? (__ldg(&gd.y[gi]) - gd.mean) - accw[gi] : 0.0;
         }
         __syncthreads();
-        Coords cd; cd.zr = sl_col; cd.zc = sl_col; cd.N = N; cd.d = d; cd.family = gd.family;
+        Coords cd; cd.tab = etab; cd.zr = sl_col; cd.zc = sl_col; cd.N = N; cd.d = d; cd.family = gd.family;
         build_tile(Td, cd, h, K, K);
         __syncthreads();
+        PHE(1);
+        PHB(2);
         if (K > 0) {
             double acc[4][2][2];
             acc_load(acc, Td, wt);
@@ -91,6 +97,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             acc_store(acc, Td, wt);
             __syncthreads();
         }
+        PHE(2);
+        PHB(3);
         // First group of panel tiles of this column: slots reserved now, covariance entries generated
         // by warps 2..7 in the shadow of the serial 8x8 factorisations of the diagonal tile
         // (6 half-strips of 4 rows per 8-column step => 3 tiles per diagonal tile).
@@ -110,12 +118,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             }
         }
         __syncthreads();
+        PHE(3);
         auto shadow = [&](int jb, int v) {
             const int hs = 6 * jb + v;                 // half-strip index: tile hs / 16, rows 4 * (hs % 16) ..
             const int q = hs >> 4;
             if (q < ng0) {
                 double* T = (q == 0) ? Tt0[0] : ((q == 1) ? Tt0[1] : Tt0[2]);
-                Coords cp; cp.zr = sl_row + q * SL; cp.zc = sl_col; cp.N = N; cp.d = d; cp.family = gd.family;
+                Coords cp; cp.tab = etab; cp.zr = sl_row + q * SL; cp.zc = sl_col; cp.N = N; cp.d = d; cp.family = gd.family;
                 build_rows(T, cp, h, K + 1 + q, K, 4 * (hs & 15), 4);
             }
         };
@@ -139,8 +148,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                 if (p == 0) zl[row] = zz;
                 __syncwarp();
             };
+            PHB(4);
             tile_potrf(Td, dinv, rinv, fail, hook, shadow);
+            PHE(4);
         }
+        PHB(7);
         if (*fail && first_fail == 0) first_fail = TS * K + *fail;
         if (tid < TS && TS * K + tid < N) {
             part[0] += log(Td[tix(tid, tid)]);
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
             __syncthreads();
             if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(K, K) * TILE_ELEMS, Td, TILE_BYTES);
         }
+        PHE(7);
         // ================= panel tiles (I, K), I > K, in groups of up to gb =================
         for (int I0 = K + 1; I0 < NT; I0 += gb) {
             const int ng = min(gb, NT - I0);
@@ -168,15 +181,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                     if (prebuilt) {
                         st[q] = st0[q]; Tt[q] = Tt0[q];
                     } else {
+                        PHB(8);
                         st[q] = tc.alloc(tile_id(0, I, K), dead, pins);     // (block barrier inside)
                         pins |= pin(st[q]);
                         Tt[q] = tc.ptr(st[q]);
                         stage_slice(sl_row, gd, h, I);
                         __syncthreads();
-                        Coords cp; cp.zr = sl_row; cp.zc = sl_col; cp.N = N; cp.d = d; cp.family = gd.family;
+                        Coords cp; cp.tab = etab; cp.zr = sl_row; cp.zc = sl_col; cp.N = N; cp.d = d; cp.family = gd.family;
                         build_tile(Tt[q], cp, h, I, K);
                         __syncthreads();
+                        PHE(8);
                     }
+                    PHB(9);
                     if (K > 0) {
                         double acc[4][2][2];
                         acc_load(acc, Tt[q], wt);
@@ -187,10 +203,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                         }
                         acc_store(acc, Tt[q], wt);
                     }
+                    PHE(9);
                 }
             }
+            PHB(10);
             __syncthreads();
             tile_trsm_right_multi<FACTOR_GB>(Tt, ng, Td, dinv);
+            PHE(10);
+            PHB(11);
             // accw_I += L_IK z_K   (warp w: rows 8w..8w+7, lanes across columns; lane 0 owns the row's entry)
             const double z0 = zl[lane], z1 = zl[lane + 32];
 #pragma unroll
@@ -205,6 +225,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                     }
                 }
             }
+            PHE(11);
+            PHB(12);
             if (a.store) {
                 fence_proxy_async();
                 __syncthreads();
@@ -212,9 +234,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
                     for (int q = 0; q < ng; ++q)
                         bulk_s2g(Lw + (size_t)tri_index(I0 + q, K) * TILE_ELEMS, Tt[q], TILE_BYTES);
             }
+            PHE(12);
         }
         __syncthreads();
     }
+    PHB(13);
 
     // ---- log-likelihood ----
     block_sum<2>(part, red);
@@ -226,6 +250,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_factor_kernel(FactorArgs a) {
         a.info[b] = inf;
         bulk_s2g_wait_all();
     }
+    PHE(13);
+    PHE(0);
 }
 
 }  // namespace fab

@@ -33,7 +33,8 @@ struct GradArgs {
 
 __host__ __device__ inline size_t grad_smem_bytes(int nslot, int d, int resident_np) {
     const size_t coords = resident_np ? (size_t)(d + 2) * resident_np : (size_t)(2 * (d + 1) * TS + 2 * TS);
-    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(2 * 512 + 512 + 128) + 8 * coords + 8 * (MAX_SLOTS + 2) + 64;
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(2 * 512 + 512 + 128) + 8 * coords + 8 * (MAX_SLOTS + 2) + 64 +
+           8 * EXP_TAB_N;
 }
 
 // alpha_J += T^T z_I for one 64x64 tile T (rows = block I, cols = block J); alpha lives in the HBM
@@ -68,7 +69,8 @@ template <int DD>
 __device__ __forceinline__ void contract_tile(const double (&acc)[4][2][2], double (&gacc)[MAX_PK + 1],
                                               const double* zr_s, const double* zc_s, const double* ur_s,
                                               const double* uc_s, const double* al_r, const double* al_c, int ldz,
-                                              const Hyper& h, int N, int family, int I, int J, WarpTile wt) {
+                                              const Hyper& h, int N, int family, int I, int J, WarpTile wt,
+                                              const double* __restrict__ etab) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const bool interior = TS * I + TS <= N && TS * J + TS <= N;
     const bool basis = family == 1;
@@ -114,7 +116,7 @@ __device__ __forceinline__ void contract_tile(const double (&acc)[4][2][2], doub
                         r2 += tk[k];
                     }
                     double m, gf;
-                    matern52(r2, m, gf);
+                    matern52_fast(r2, m, gf, etab);
                     const double uu = ur * (e ? uc.y : uc.x);
                     const double beta = basis ? (uu + h.cb) : 1.0;
                     const double wa = wij * h.amp;
@@ -162,7 +164,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
     double* al_all = us_all + Np;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(
         cbase + (a.resident ? (size_t)(d + 2) * Np : (size_t)(2 * SL + 2 * TS)));   // MAX_SLOTS + 2 mbarriers
+    double* etab = reinterpret_cast<double*>(bars + MAX_SLOTS + 2 + 6);             // exp table (fast Matern evaluation)
 
+    PHB(20); PHB(21);
     const Hyper h = decode_hyper(gd, a.theta + (size_t)b * Pk, a.yerr2[b]);
     double* Lw = a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS;
     const double* Dw = a.wk.Dinv + (size_t)b * NT * 512;
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
         return;
     }
     for (int i = tid; i < Np; i += NTHREADS) alg[i] = 0.0;
+    exp_table_fill(etab);
     if (a.resident) {
         for (int e = tid; e < N * gd.D; e += NTHREADS) {
             const int i = e / gd.D, k = e - i * gd.D;
@@ -199,7 +204,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
 #pragma unroll
     for (int k = 0; k <= MAX_PK; ++k) gacc[k] = 0.0;
 
+    PHE(21);
     for (int i = 0; i < a.nops; ++i) {
+        PHB(22);
         const TileOp* opp = a.prog + i;
         const int type = __ldg(&opp->type), I = __ldg(&opp->I), J = __ldg(&opp->J), k = __ldg(&opp->k);
         const int sA = __ldg(&opp->slotA), sB = __ldg(&opp->slotB), sC = __ldg(&opp->slotC);
@@ -224,28 +231,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
                 phases ^= 1u << s;
             }
         }
+        PHE(22);
         const double* A = slots + (size_t)sA * TILE_ELEMS;
         if (type == OP_INV_DIAG) {
             double* C = slots + (size_t)sC * TILE_ELEMS;
+            PHB(23);
             tile_trsm_left<true, false>(C, A, dinvb + dbuf * 512);
+            PHE(23); PHB(24);
             tile_matvec_t(C, zg + TS * J, alg + TS * J, part);
+            PHE(24); PHB(25);
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(J, J) * TILE_ELEMS, C, TILE_BYTES);
+            PHE(25);
         } else if (type == OP_P1_MMA) {
+            PHB(26);
             if (flags & OPF_FIRST) acc_zero(acc);
             // W_JJ is lower triangular: rows k' < n contribute nothing
             tile_mma<false, false, false>(acc, A, slots + (size_t)sB * TILE_ELEMS, wt, (k == J) ? wt.n0 : 0, TS);
+            PHE(26);
         } else if (type == OP_P1_FIN) {
             double* C = slots + (size_t)sC * TILE_ELEMS;
+            PHB(27);
             acc_store(acc, C, wt);
             __syncthreads();
             tile_trsm_left<false, true>(C, A, dinvb + dbuf * 512);
+            PHE(27); PHB(24);
             tile_matvec_t(C, zg + TS * I, alg + TS * J, part);
+            PHE(24); PHB(25);
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) bulk_s2g(Lw + (size_t)tri_index(I, J) * TILE_ELEMS, C, TILE_BYTES);
+            PHE(25);
         } else {   // OP_P2_MMA
+            PHB(28);
             if (a.resident) {
                 if (i == 0 || (__ldg(&(opp - 1)->type) != OP_P2_MMA)) {       // first phase-2 operation: alpha is final
                     for (int q = tid; q < Np; q += NTHREADS) al_all[q] = alg[q];
@@ -260,7 +279,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
             if (flags & OPF_FIRST) acc_zero(acc);
             // W_II is lower triangular: (W_II)[k'][m] = 0 for k' < m
             tile_mma<true, false, false>(acc, A, slots + (size_t)sB * TILE_ELEMS, wt, (k == I) ? wt.m0 : 0, TS);
+            PHE(28);
             if (flags & OPF_LAST) {
+                PHB(29);
                 if (!a.resident && (flags & OPF_NEW_PAIR)) __syncthreads();      // slices staged in this very operation
                 const double* zr_p = a.resident ? zs_all + TS * I : sl_r;
                 const double* zc_p = a.resident ? zs_all + TS * J : sl_c;
@@ -269,15 +290,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
                 const double* ar_p = a.resident ? al_all + TS * I : al_r;
                 const double* ac_p = a.resident ? al_all + TS * J : al_c;
                 const int ldz = a.resident ? Np : TS;
-#define FAB_CONTRACT_CASE(DD) case DD: contract_tile<DD>(acc, gacc, zr_p, zc_p, ur_p, uc_p, ar_p, ac_p, ldz, h, N, gd.family, I, J, wt); break;
+#define FAB_CONTRACT_CASE(DD) case DD: contract_tile<DD>(acc, gacc, zr_p, zc_p, ur_p, uc_p, ar_p, ac_p, ldz, h, N, gd.family, I, J, wt, etab); break;
                 switch (d) {
                     FAB_CONTRACT_CASE(1) FAB_CONTRACT_CASE(2) FAB_CONTRACT_CASE(3) FAB_CONTRACT_CASE(4)
                     FAB_CONTRACT_CASE(5) FAB_CONTRACT_CASE(6) FAB_CONTRACT_CASE(7) FAB_CONTRACT_CASE(8)
                 }
 #undef FAB_CONTRACT_CASE
+                PHE(29);
             }
         }
     }
+    PHB(30);
     __syncthreads();
     if (!a.grad) {
         if (tid == 0) bulk_s2g_wait_all();
@@ -295,6 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_grad_kernel(GradArgs a) {
         go[Pk] = 0.5 * gacc[MAX_PK];
         bulk_s2g_wait_all();
     }
+    PHE(30); PHE(20);
 }
 
 }  // namespace fab

@@ -22,6 +22,17 @@ namespace fab {
 #define FAB_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #endif
 
+// Optional per-phase cycle counters (development builds only: -DFAB_PHASE_PROF, tools/phase_prof.py).
+// Thread 0 of CTA 0 brackets a region with PHB(id) / PHE(id); both are fire-and-forget reductions.
+#if defined(FAB_PHASE_PROF) && !defined(FAB_CUSIM)
+__device__ long long g_phase[64];
+#define PHB(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
+#define PHE(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
+#else
+#define PHB(id) do {} while (0)
+#define PHE(id) do {} while (0)
+#endif
+
 constexpr double kTiny = 1.25e-12;        // george's default white noise (oracle/george_oracle.py TINY)
 constexpr double kLog2Pi = 1.8378770664093453;
 

@@ -212,14 +212,17 @@ __device__ __forceinline__ void tile_potrf(double* A, double* dinv, double* rinv
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     for (int jb = 0; jb < 8; ++jb) {
         if (threadIdx.x == 0) {
+            PHB(5);
             const int f = potrf8(A, jb, rinv);
             if (f && *fail == 0) *fail = f;
+            PHE(5);
         } else if (w == 1) {
             if (jb > 0) hook(jb - 1);
         } else if (w >= 2) {
             shadow(jb, w - 2);               // independent work of warps 2..7 in the shadow of the serial chain
         }
         __syncthreads();
+        PHB(6);
         if (w == 7) {
             // 8x8 inverse for later consumers (panel solves, hook(jb)): off the critical path, it
             // spans phases (b) and (c) of the other seven warps
@@ -275,6 +278,7 @@ __device__ __forceinline__ void tile_potrf(double* A, double* dinv, double* rinv
             }
         }
         __syncthreads();
+        PHE(6);
     }
     if (w == 1) hook(7);
     __syncthreads();
