@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "GP loglik+grad evals/sec (N=256, 128 walkers/GPU)"
+# dram__bytes_read.sum + dram__bytes_write.sum of one gp_dag_kernel launch from the committed ncu --set full
+# capture (profiles/); None until a capture of the current kernel exists.
+TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_SOURCE = None
 UNIT = "evals/s"
 CONFIG_ID = 2
 
@@ -37,14 +41,16 @@ CONFIG_ID = 2
 # CPU oracle timing (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    cfg, lo, hi = args
+    cfg, lo, hi = args                      # evaluates walkers lo .. hi-1 (indices taken modulo the batch)
     from threadpoolctl import threadpool_limits
     from fabolas_b200.workloads import gp_workload
     from oracle import george_oracle as go
     w = gp_workload(cfg)
+    B = w["theta"].shape[0]
+    idx = np.arange(lo, hi) % B
     with threadpool_limits(1):
         t0 = time.perf_counter()
-        go.loglik_batch(w["family"], w["X"], w["y"], w["mean"], w["theta"][lo:hi], w["yerr2"][lo:hi], grad=True,
+        go.loglik_batch(w["family"], w["X"], w["y"], w["mean"], w["theta"][idx], w["yerr2"][idx], grad=True,
                         amp_axes=int(w["amp_mult"]))
         return time.perf_counter() - t0
 
@@ -56,7 +62,6 @@ def cpu_oracle_rate(per_core: int, cores: int | None = None, pool=None):
     from fabolas_b200.workloads import gp_workload
     B = gp_workload(CONFIG_ID)["theta"].shape[0]
     jobs = [(CONFIG_ID, (i * per_core) % B, (i * per_core) % B + per_core) for i in range(cores)]
-    jobs = [(c, lo, min(hi, B)) if hi <= B else (c, 0, per_core) for (c, lo, hi) in jobs]
     own = pool is None
     if own:
         pool = mp.get_context("spawn").Pool(cores)
@@ -233,8 +238,15 @@ def run_ours(args):
         eng.loglik(theta_d, yerr2_d, grad=True)
         kt.append(eng.get_timing())
     eng.set_timing(False)
-    kt = np.array(kt)
-    ms_factor, ms_grad = float(np.mean(kt[:, 0])), float(np.mean(kt[:, 1]))
+    ms_kernel = float(np.mean(np.array(kt)[:, 0]))        # one fused kernel per step (gp_dag_kernel, mode GRAD)
+    kt = []
+    eng.set_timing(True)
+    for _ in range(max(10, K // 2)):
+        flush.zero_()
+        eng.loglik(theta_d, yerr2_d, grad=False)
+        kt.append(eng.get_timing())
+    eng.set_timing(False)
+    ms_ll_only = float(np.mean(np.array(kt)[:, 0]))       # the MCMC inner loop proper: log-likelihood without gradient
 
     # ---- second headline number: Entropy-Search acquisition evaluations per second (BASELINE configs[2]) ----
     # Z = 50 representers, I = 20 innovations, 2048 candidates per GPU x 128 hyper-samples at N = 256.
@@ -306,11 +318,11 @@ def run_ours(args):
         except Exception:
             pass
         f_ll, f_llg = flops_ll(N, d), flops_llg(N, d, P)
-        grad_tf = Bg * (f_llg - f_ll) / (ms_grad * 1e-3) / 1e12
-        factor_tf = Bg * f_ll / (ms_factor * 1e-3) / 1e12
+        kern_tf = Bg * f_llg / (ms_kernel * 1e-3) / 1e12
+        ll_tf = Bg * f_ll / (ms_ll_only * 1e-3) / 1e12
         cpu_val, cores, n_evals, cpu_dt = (None, None, None, None)
         if world == 1 and not args.no_cpu:
-            cpu_val, cores, n_evals, cpu_dt = cpu_oracle_rate(per_core=48)
+            cpu_val, cores, n_evals, cpu_dt = cpu_oracle_rate(per_core=args.cpu_per_core)
         ms_step = ms_total / K
         out = {
             "metric": METRIC, "value": world * Bg / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
@@ -323,15 +335,18 @@ def run_ours(args):
             "e2e": {"value": world * Bg / (ms_e2e / K * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(theta_h.numel() * 8 + yerr2_h.numel() * 8),
                     "d2h_bytes_per_step": int(ll_host.numel() * 8 + g_host.numel() * 8)},
-            "gpu_launches": 2 * K,
+            "gpu_launches": K,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "gp_grad_kernel", "achieved": grad_tf, "peak": peak,
-                         "unit": "TFLOP/s", "frac": grad_tf / peak, "traffic": None,
+            "roofline": {"bound": "tensor", "pipe": "FP64 tensor cores (DMMA mma.sync m8n8k4.f64; tcgen05 has no FP64 kind)",
+                         "kernel": "gp_dag_kernel", "achieved": kern_tf, "peak": peak,
+                         "unit": "TFLOP/s", "frac": kern_tf / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                         "traffic_source": TRAFFIC_SOURCE,
                          "peak_source": "measured DMMA m8n8k4 peak on this pool (profiles/r01_fp64_peaks.json); "
+                                        "MEASURED_PEAKS.json carries no FP64 figure; "
                                         f"live cuBLAS DGEMM 4096^3 = {dgemm_tf:.2f} TFLOP/s",
-                         "flops_per_eval": f_llg - f_ll, "ms_per_launch": ms_grad,
-                         "factor_kernel": {"achieved": factor_tf, "frac": factor_tf / peak, "ms_per_launch": ms_factor,
-                                           "flops_per_eval": f_ll},
+                         "flops_per_eval": f_llg, "evals_per_launch": Bg, "ms_per_launch": ms_kernel,
+                         "ll_only": {"evals_per_s": Bg / (ms_ll_only * 1e-3), "ms_per_launch": ms_ll_only,
+                                     "flops_per_eval": f_ll, "achieved": ll_tf, "frac": ll_tf / peak},
                          "whole_step_frac": Bg * f_llg / (ms_step * 1e-3) / 1e12 / peak},
             "es_acquisition": es_out,
             "cpu_baseline": None if cpu_val is None else {
@@ -352,6 +367,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg (profiling runs)")
+    ap.add_argument("--cpu-per-core", type=int, default=640,
+                    help="ll+grad evaluations per host core of the bounded CPU-oracle sample (~10-30 s of CPU work)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -2,13 +2,16 @@
 #include "../../include/fabolas_b200.h"
 #include "gp_factor.cuh"
 #include "gp_grad.cuh"
+#include "gp_dag.cuh"
 #include "gp_predict.cuh"
 #include "epmgp.cuh"
 #include "ig.cuh"
 #include "kmat.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -45,6 +48,11 @@ struct fab_ctx {
     TileOp* dProg[2] = {nullptr, nullptr};
     int progN[2] = {0, 0}, progNT[2] = {-1, -1}, progSlots[2] = {-1, -1};
     std::vector<TileOp> hProg[2];
+    // fused warp-specialised kernel (gp_dag.cuh): cached static programs per (NT, slots, mode)
+    struct DagDev { DagOp* bulk = nullptr; DagOp* chain = nullptr; int nbulk = 0, nchain = 0; DagProgram host; };
+    std::map<long long, DagDev> dag;
+    double* wkSpill = nullptr; size_t capSpill = 0;
+    bool legacy = false;         // FAB_LEGACY=1: the two-kernel path (gp_factor_kernel + gp_grad_kernel)
     int smem_optin = 232448;
     int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
     int force_slices = 0;        // test knob: never keep all coordinates resident in the gradient kernel
@@ -116,12 +124,15 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
         c->smem_optin = v;
     cudaFuncSetAttribute(gp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(gp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(gp_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(gp_predict_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(epmgp_ep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(epmgp_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(es_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(gp_predict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
 #endif
+    const char* lg = getenv("FAB_LEGACY");
+    c->legacy = lg && lg[0] == '1';
     *out = c;
     return FAB_OK;
 }
@@ -137,6 +148,8 @@ int fab_ctx_destroy(fab_ctx* c) {
 #ifndef FAB_CUSIM
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 #endif
+    for (auto& kv : c->dag) { cudaFree(kv.second.bulk); cudaFree(kv.second.chain); }
+    cudaFree(c->wkSpill);
     cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw); cudaFree(c->dProg[0]); cudaFree(c->dProg[1]);
     delete c;
     return FAB_OK;
@@ -268,12 +281,62 @@ static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int
     return FAB_OK;
 }
 
+// One launch of the fused kernel.  mode: DAG_LL (ll only), DAG_FACTOR (+ L tiles in the workspace),
+// DAG_FIT (+ W = L^-1 tiles and alpha in the workspace), DAG_GRAD (+ gradient).
+static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info, double* grad,
+                      int mode) {
+    const GpData& gd = c->gd;
+    const int ntiles = gd.NT * (gd.NT + 1) / 2;
+    int nslot = c->max_slots;
+    int resident = (!c->force_slices && dag_smem_bytes(nslot, gd.d, gd.Np) <= (size_t)c->smem_optin) ? 1 : 0;
+    while (nslot > 0 && dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0) > (size_t)c->smem_optin) --nslot;
+    if (nslot < 4) return fail(c, FAB_EUNSUPPORTED, "not enough shared memory for the fused kernel");
+    const long long key = ((long long)gd.NT << 16) | (nslot << 4) | mode;
+    auto it = c->dag.find(key);
+    if (it == c->dag.end()) {
+        fab_ctx::DagDev dv;
+        dv.host = build_dag_program(gd.NT, nslot, mode);
+        if (!dv.host.ok) return fail(c, FAB_EUNSUPPORTED, dv.host.err.c_str());
+        dv.nbulk = (int)dv.host.bulk.size(); dv.nchain = (int)dv.host.chain.size();
+        if (cudaMalloc(reinterpret_cast<void**>(&dv.bulk), (dv.nbulk + 1) * sizeof(DagOp)) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&dv.chain), (dv.nchain + 1) * sizeof(DagOp)) != cudaSuccess)
+            return fail(c, FAB_ENOMEM, "tile program allocation failed");
+        it = c->dag.emplace(key, std::move(dv)).first;          // host vectors stay alive: async copy sources
+        FAB_CUDA(c, cudaMemcpyAsync(it->second.bulk, it->second.host.bulk.data(), it->second.nbulk * sizeof(DagOp),
+                                    cudaMemcpyHostToDevice, c->stream));
+        FAB_CUDA(c, cudaMemcpyAsync(it->second.chain, it->second.host.chain.data(), it->second.nchain * sizeof(DagOp),
+                                    cudaMemcpyHostToDevice, c->stream));
+    }
+    const fab_ctx::DagDev& dv = it->second;
+    int rc;
+    if ((rc = ensure(c, &c->wk.Lw, &c->capL, (size_t)B * ntiles * TILE_ELEMS)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->wk.accw, &c->capW, (size_t)B * gd.Np)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->wk.zvec, &c->capZ, (size_t)B * gd.Np)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->wk.alpha, &c->capA, (size_t)B * gd.Np)) != FAB_OK) return rc;
+    if (mode == DAG_FACTOR && (rc = ensure(c, &c->wkSpill, &c->capSpill, (size_t)B * gd.NT * TILE_ELEMS)) != FAB_OK) return rc;
+    DagArgs a;
+    a.gd = gd; a.wk = c->wk; a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info; a.grad = grad;
+    a.bulk = dv.bulk; a.chain = dv.chain; a.nbulk = dv.nbulk; a.nchain = dv.nchain;
+    a.nslot = nslot; a.mode = mode; a.resident = resident; a.ntiles = ntiles; a.wk_spill = c->wkSpill;
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
+    FAB_LAUNCH(gp_dag_kernel, B, DAG_THREADS, dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0), c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
+    c->resident = false;
+    c->es_ready = false;
+    c->wsB = B;
+    c->factored = mode == DAG_FACTOR;
+    c->inverted = mode == DAG_FIT;
+    return FAB_OK;
+}
+
 int fab_gp_loglik_batch(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, double* grad,
                         int* info) {
     if (!c) return FAB_EINVAL;
     if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
     if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->legacy) return launch_dag(c, theta, yerr2, B, ll, info, grad, grad ? DAG_GRAD : DAG_LL);
     int rc = launch_factor(c, theta, yerr2, B, ll, info, grad != nullptr);
     if (rc != FAB_OK) return rc;
     if (grad) return launch_grad(c, theta, yerr2, B, grad, info);
@@ -285,6 +348,7 @@ int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2,
     if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
     if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->legacy) return launch_dag(c, theta, yerr2, B, ll, info, nullptr, DAG_FACTOR);
     int rc = launch_factor(c, theta, yerr2, B, ll, info, true);
     if (rc != FAB_OK) return rc;
     return FAB_OK;
@@ -292,7 +356,12 @@ int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2,
 
 // factorize + W = L^-1 + alpha, hyper-parameters copied into the context: models become resident.
 int fab_gp_fit_batch(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info) {
-    int rc = fab_gp_factorize_batch(c, theta, yerr2, B, ll, info);
+    if (!c) return FAB_EINVAL;
+    if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
+    if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    int rc = c->legacy ? fab_gp_factorize_batch(c, theta, yerr2, B, ll, info)
+                       : launch_dag(c, theta, yerr2, B, ll, info, nullptr, DAG_FIT);
     if (rc != FAB_OK) return rc;
     const GpData& gd = c->gd;
     if ((rc = ensure(c, &c->dTheta, &c->capT, (size_t)B * gd.Pk)) != FAB_OK) return rc;
@@ -301,8 +370,10 @@ int fab_gp_fit_batch(fab_ctx* c, const double* theta, const double* yerr2, int B
     FAB_CUDA(c, cudaMemcpyAsync(c->dTheta, theta, sizeof(double) * B * gd.Pk, cudaMemcpyDeviceToDevice, c->stream));
     FAB_CUDA(c, cudaMemcpyAsync(c->dYerr2, yerr2, sizeof(double) * B, cudaMemcpyDeviceToDevice, c->stream));
     FAB_CUDA(c, cudaMemcpyAsync(c->dInfo, info, sizeof(int) * B, cudaMemcpyDeviceToDevice, c->stream));
-    rc = launch_grad(c, c->dTheta, c->dYerr2, B, nullptr, c->dInfo);
-    if (rc != FAB_OK) return rc;
+    if (c->legacy) {
+        rc = launch_grad(c, c->dTheta, c->dYerr2, B, nullptr, c->dInfo);
+        if (rc != FAB_OK) return rc;
+    }
     c->resident = true;
     return FAB_OK;
 }

@@ -28,9 +28,13 @@ namespace fab {
 __device__ long long g_phase[64];
 #define PHB(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
 #define PHE(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
+#define PHBC(id) do { if (threadIdx.x == 256 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
+#define PHEC(id) do { if (threadIdx.x == 256 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
 #else
 #define PHB(id) do {} while (0)
 #define PHE(id) do {} while (0)
+#define PHBC(id) do {} while (0)
+#define PHEC(id) do {} while (0)
 #endif
 
 constexpr double kTiny = 1.25e-12;        // george's default white noise (oracle/george_oracle.py TINY)
