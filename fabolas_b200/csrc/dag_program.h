@@ -59,6 +59,8 @@ struct DagOp {             // 28 ints, read by every thread of its stream
     int pad[3];
 };
 
+static_assert(sizeof(DagOp) == 112, "DagOp is read as int4 words by the kernel");
+
 struct DagProgram {
     std::vector<DagOp> bulk, chain;
     int NT = 0, nslot = 0, mode = 0;

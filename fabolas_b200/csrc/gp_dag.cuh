@@ -20,7 +20,7 @@
 namespace fab {
 
 constexpr int DAG_BULK_THREADS = NTHREADS;         // warps 0..7
-constexpr int DAG_THREADS = NTHREADS + 32;         // + the chain warp
+constexpr int DAG_THREADS = NTHREADS + 32 * NCW;   // + the chain warps
 
 struct DagArgs {
     GpData gd;
@@ -41,7 +41,7 @@ struct DagArgs {
 
 __host__ __device__ inline size_t dag_smem_bytes(int nslot, int d, int resident_np) {
     const size_t coords = resident_np ? (size_t)(d + 4) * resident_np : (size_t)(2 * (d + 1) * TS + 2 * TS);
-    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + EXP_TAB_N + 512 + 128 + 64 + 64 + 16) + 8 * coords +
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + EXP_TAB_N + 512 + 128 + 64 + 64 + 64 + 4 * TS) + 8 * coords +
            8 * MAX_SLOTS + 64;
 }
 
@@ -67,82 +67,149 @@ __device__ __forceinline__ void spin_until(int* p, int target) {
 #endif
 }
 
-// Covariance tile (I, J) straight into the DMMA accumulator fragment layout (16 entries per thread,
-// all independent: the Matern evaluations overlap).  Padding rows/columns get the identity; for a
-// diagonal tile the strictly-upper 8x8 blocks are zero.
+// Covariance tile (I, J) straight into the DMMA accumulator fragment layout (16 entries per thread).
+// Four passes of four entries (two rows x two adjacent columns) keep the register footprint small enough
+// for the four Matern chains of a pass to overlap; evaluation is branch-free (padding and the strictly-upper
+// blocks of a diagonal tile are selected afterwards: identity resp. zero).
 template <int DD>
 __device__ __forceinline__ void build_acc(double (&acc)[4][2][2], const double* zr_s, const double* zc_s,
                                           const double* ur_s, const double* uc_s, int ldz, const Hyper& h, int N,
                                           int family, int I, int J, WarpTile wt, const double* __restrict__ etab) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const bool interior = TS * I + TS <= N && TS * J + TS <= N;
     const bool basis = family == 1;
-    double zr[4][DD], ur[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int li = wt.m0 + 8 * i + g;
-#pragma unroll
-        for (int k = 0; k < DD; ++k) zr[i][k] = zr_s[k * ldz + li];
-        ur[i] = ur_s[li] * h.inv_g2;
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    const double cb = basis ? h.cb : 1.0;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int ip = q >> 1, j = q & 1;
         const int lj0 = wt.n0 + 8 * j + 2 * t;
         const int bcol = (wt.n0 >> 3) + j;
         double2 zc[DD];
 #pragma unroll
         for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
         const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
+        double tmp[2][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int li = wt.m0 + 8 * i + g;
+        for (int r = 0; r < 2; ++r) {
+            const int li = wt.m0 + 8 * (2 * ip + r) + g;
             const int gi = TS * I + li;
-            const int brow = (wt.m0 >> 3) + i;
+            const bool upper = I == J && bcol > (li >> 3);
+            double zr[DD];
+#pragma unroll
+            for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
+            const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int gj = TS * J + lj0 + e;
-                double v;
-                if (I == J && bcol > brow) {
-                    v = 0.0;
-                } else if (!interior && (gi >= N || gj >= N)) {
-                    v = (gi == gj) ? 1.0 : 0.0;
-                } else {
-                    double r2 = 0.0;
+                double r2 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < DD; ++k) {
-                        const double dz = zr[i][k] - (e ? zc[k].y : zc[k].x);
-                        r2 = fma(dz, dz, r2);
-                    }
-                    v = h.amp * matern52_fast_value(r2, etab);
-                    if (basis) v *= fma(ur[i], e ? uc.y : uc.x, h.cb);
-                    if (gi == gj) v += h.diag_add;
+                for (int k = 0; k < DD; ++k) {
+                    const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                    r2 = fma(dz, dz, r2);
                 }
-                acc[i][j][e] = v;
+                double v = h.amp * matern52_fast_value(r2, etab) * fma(ur, e ? uc.y : uc.x, cb);
+                v = (gi == gj) ? v + h.diag_add : v;
+                v = (gi >= N || gj >= N) ? ((gi == gj) ? 1.0 : 0.0) : v;
+                tmp[r][e] = upper ? 0.0 : v;
             }
+        }
+        switch (q) {                        // static accumulator indices
+        case 0: acc[0][0][0] = tmp[0][0]; acc[0][0][1] = tmp[0][1]; acc[1][0][0] = tmp[1][0]; acc[1][0][1] = tmp[1][1]; break;
+        case 1: acc[0][1][0] = tmp[0][0]; acc[0][1][1] = tmp[0][1]; acc[1][1][0] = tmp[1][0]; acc[1][1][1] = tmp[1][1]; break;
+        case 2: acc[2][0][0] = tmp[0][0]; acc[2][0][1] = tmp[0][1]; acc[3][0][0] = tmp[1][0]; acc[3][0][1] = tmp[1][1]; break;
+        default: acc[2][1][0] = tmp[0][0]; acc[2][1][1] = tmp[0][1]; acc[3][1][0] = tmp[1][0]; acc[3][1][1] = tmp[1][1]; break;
         }
     }
 }
 
-// Sum of NV per-thread values over the 256 bulk threads (named barrier 1); result valid in every bulk thread.
-template <int NV>
-__device__ __forceinline__ void bulk_sum(double (&v)[NV], double* scratch) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// Contract one 64x64 tile of (alpha alpha^T - K^-1), held in this warp's DMMA accumulator fragment, with
+// dK/dtheta regenerated from the coordinates: branch-free (weights select what counts), four entries per
+// pass as in build_acc.  Diagonal tiles: weight 2 below the diagonal 8x8 blocks, 1 on them, 0 above.
+// The nine partial sums of the warp go to gsum[warp][.] (fixed order => deterministic):
+//   [0] log_c0, [1..DD] log_M_k, [MAX_D+1] log_gamma2, [MAX_D+2] log_cb, [MAX_PK] yerr2.
+template <int DD>
+__device__ __forceinline__ void contract_acc(const double (&acc)[4][2][2], double* gsum_w,
+                                             const double* zr_s, const double* zc_s, const double* ur_s,
+                                             const double* uc_s, const double* al_r, const double* al_c, int ldz,
+                                             const Hyper& h, int N, int family, int I, int J, WarpTile wt,
+                                             const double* __restrict__ etab) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const bool basis = family == 1;
+    const double cb = basis ? h.cb : 1.0;
+    double gm[DD];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const double s = warp_sum(v[i]);
-        if (lane == 0) scratch[i * NWARPS + w] = s;
+    for (int k = 0; k < DD; ++k) gm[k] = 0.0;
+    double g0 = 0.0, gg2 = 0.0, gcb = 0.0, gtr = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int ip = q >> 1, j = q & 1;
+        const int lj0 = wt.n0 + 8 * j + 2 * t;
+        const int bcol = (wt.n0 >> 3) + j;
+        double kinv[2][2];
+        switch (q) {                        // static accumulator indices
+        case 0: kinv[0][0] = acc[0][0][0]; kinv[0][1] = acc[0][0][1]; kinv[1][0] = acc[1][0][0]; kinv[1][1] = acc[1][0][1]; break;
+        case 1: kinv[0][0] = acc[0][1][0]; kinv[0][1] = acc[0][1][1]; kinv[1][0] = acc[1][1][0]; kinv[1][1] = acc[1][1][1]; break;
+        case 2: kinv[0][0] = acc[2][0][0]; kinv[0][1] = acc[2][0][1]; kinv[1][0] = acc[3][0][0]; kinv[1][1] = acc[3][0][1]; break;
+        default: kinv[0][0] = acc[2][1][0]; kinv[0][1] = acc[2][1][1]; kinv[1][0] = acc[3][1][0]; kinv[1][1] = acc[3][1][1]; break;
+        }
+        double2 zc[DD];
+#pragma unroll
+        for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
+        const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
+        const double2 ac = *reinterpret_cast<const double2*>(&al_c[lj0]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int li = wt.m0 + 8 * (2 * ip + r) + g;
+            const int gi = TS * I + li;
+            const int brow = li >> 3;
+            double zr[DD];
+#pragma unroll
+            for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
+            const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
+            const double ar = al_r[li];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = TS * J + lj0 + e;
+                double wgt = (I != J || bcol < brow) ? 2.0 : ((bcol == brow) ? 1.0 : 0.0);
+                wgt = (gi >= N || gj >= N) ? 0.0 : wgt;
+                const double wij = wgt * (ar * (e ? ac.y : ac.x) - kinv[r][e]);
+                double r2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < DD; ++k) {
+                    const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                    r2 = fma(dz, dz, r2);
+                }
+                double m, gf;
+                matern52_fast(r2, m, gf, etab);
+                const double uu = ur * (e ? uc.y : uc.x);
+                const double beta = uu + cb;
+                const double wa = wij * h.amp;
+                const double wam = wa * m;
+                g0 = fma(wam, beta, g0);
+                const double wg = wa * beta * gf;
+#pragma unroll
+                for (int k = 0; k < DD; ++k) {          // dz^2 recomputed: cheaper than keeping it across the Matern chain
+                    const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                    gm[k] = fma(wg * dz, dz, gm[k]);
+                }
+                gg2 = fma(-wam, uu, gg2);
+                gcb = fma(wam, cb, gcb);
+                gtr += (gi == gj) ? wij : 0.0;
+            }
+        }
     }
-    named_bar_sync(1, DAG_BULK_THREADS);
+    g0 = warp_sum(g0); gg2 = warp_sum(gg2); gcb = warp_sum(gcb); gtr = warp_sum(gtr);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double s = 0.0;
-        for (int k = 0; k < NWARPS; ++k) s += scratch[i * NWARPS + k];
-        v[i] = s;
+    for (int k = 0; k < DD; ++k) gm[k] = warp_sum(gm[k]);
+    if (lane == 0) {
+        gsum_w[0] += g0;
+#pragma unroll
+        for (int k = 0; k < DD; ++k) gsum_w[1 + k] += gm[k];
+        if (basis) { gsum_w[MAX_D + 1] += gg2; gsum_w[MAX_D + 2] += gcb; }
+        gsum_w[MAX_PK] += gtr;
     }
 }
 
-// 288 threads: the register file is allocated in groups of four warps, so the budget is that of 384
-// threads (168 registers each) -- what ptxas assumes under __launch_bounds__(288).
+// 12 warps: 65536 / 384 = 170 -> 168 registers per thread.
 #define FAB_DAG_KERNEL_ATTR __global__ void __launch_bounds__(DAG_THREADS, 1)
 FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     FAB_DYN_SMEM(smem_raw);
@@ -159,8 +226,9 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     double* red = part + 512;                                 // 128: final reductions
     double* crhs = red + 128;                                 // 64: chain right-hand side
     double* cz = crhs + 64;                                   // 64: chain z_K
-    double* rinv = cz + 64;                                   // 8 (+8)
-    double* cbase = rinv + 16;
+    double* rinv = cz + 64;                                   // 64: reciprocal pivots, 8 per 8-column step
+    double* cpart = rinv + 64;                                // 256: partial sums across the chain warps
+    double* cbase = cpart + 4 * TS;
     // resident: zs[k * Np + i] (k < d), us[i], alpha[i], z[i], accw[i];  otherwise two staged slices + alpha slices
     double* zs_all = cbase;
     double* us_all = zs_all + (size_t)d * Np;
@@ -173,9 +241,11 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     double* accw = a.resident ? zv + Np : a.wk.accw + (size_t)b * Np;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(
         cbase + (a.resident ? (size_t)(d + 4) * Np : (size_t)(2 * SL + 2 * TS)));
-    int* sync = reinterpret_cast<int*>(bars + MAX_SLOTS);     // [0] bulk warp arrivals, [1] chain ops done, [2] failure
+    int* sync = reinterpret_cast<int*>(bars + MAX_SLOTS);     // [0] bulk warp arrivals, [1] chain ops done, [2] failure, [3] per-tile failure
 
-    const Hyper h = decode_hyper(gd, a.theta + (size_t)b * Pk, a.yerr2[b]);
+    const Hyper hfull = decode_hyper(gd, a.theta + (size_t)b * Pk, a.yerr2[b]);
+    Hyper h;                              // scalars only: hfull.scale[] is indexed dynamically and lives in local memory
+    h.amp = hfull.amp; h.inv_g2 = hfull.inv_g2; h.cb = hfull.cb; h.diag_add = hfull.diag_add;
     double* Lw = a.wk.Lw ? a.wk.Lw + (size_t)b * a.ntiles * TILE_ELEMS : nullptr;
     double* Lx = a.wk_spill ? a.wk_spill + (size_t)b * gd.NT * TILE_ELEMS : nullptr;
     auto ws_tile = [&](int tile) { return tile < a.ntiles ? Lw + (size_t)tile * TILE_ELEMS : Lx + (size_t)(tile - a.ntiles) * TILE_ELEMS; };
@@ -186,7 +256,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
         for (int e = tid; e < N * gd.D; e += DAG_THREADS) {
             const int i = e / gd.D, k = e - i * gd.D;
             const double x = __ldg(&gd.X[e]);
-            if (k < d) zs_all[k * Np + i] = x * h.scale[k];
+            if (k < d) zs_all[k * Np + i] = x * hfull.scale[k];
             else us_all[i] = x;
         }
         for (int i = tid; i < Np; i += DAG_THREADS) {
@@ -196,14 +266,15 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     }
     if (tid == 0) {
         for (int s = 0; s < MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
-        sync[0] = 0; sync[1] = 0; sync[2] = 0;
+        sync[0] = 0; sync[1] = 0; sync[2] = 0; sync[3] = 0;
     }
     __syncthreads();                      // the only block-wide barrier: the two streams part here
 
-    if (w == NWARPS) {
+    if (w >= NWARPS) {
         // ======================================= CHAIN stream =======================================
+        const int cw = w - NWARPS;
         double logdet = 0.0, zz = 0.0;
-        int first_fail = 0;
+        int first_fail = 0;                   // (warp 0, lane 0)
         PHBC(55);
         for (int j = 0; j < a.nchain; ++j) {
             const DagOp* op = a.chain + j;
@@ -217,41 +288,53 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             double* A = slots + (size_t)sA * TILE_ELEMS;
             double* W = slots + (size_t)sC * TILE_ELEMS;
             PHBC(57);
-            const int f = potrf64_warp(A, dinv, rinv);
+            potrf64_chain(A, W, dinv, rinv, &sync[3], cw);
             PHEC(57);
-            if (f && first_fail == 0) first_fail = TS * K + f;
-            logdet += log(A[tix(lane, lane)]) + log(A[tix(lane + 32, lane + 32)]);
-            PHBC(58);
-            inv64_warp(W, A, dinv);
-            PHEC(58);
+            if (cw == 0 && lane == 0 && sync[3] != 0) {
+                if (first_fail == 0) first_fail = TS * K + sync[3];
+                sync[3] = 0;
+            }
+            if (lane < 16) logdet += log(A[tix(16 * cw + lane, 16 * cw + lane)]);
+            fence_proxy_async();          // W (and, in FACTOR mode, L) may be written through by a bulk store
+            chain_bar();
+            if (cw == 0 && lane == 0) sync_arrive(&sync[1]);      // event 2j + 1: L(K,K) and W(K,K) are final
             PHBC(59);
             // z_K = W_KK (r_K - sum_{J<K} L_KJ z_J)
+            if (cw == 0) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int r = lane + 32 * half, gi = TS * K + r;
-                crhs[r] = (gi < N) ? (__ldg(&gd.y[gi]) - gd.mean) - accw[gi] : 0.0;
+                for (int half = 0; half < 2; ++half) {
+                    const int r = lane + 32 * half, gi = TS * K + r;
+                    crhs[r] = (gi < N) ? (__ldg(&gd.y[gi]) - gd.mean) - accw[gi] : 0.0;
+                }
             }
-            __syncwarp();
-            double z0, z1;
-            tile_matvec_warp(W, crhs, z0, z1);
-            zz = fma(z0, z0, fma(z1, z1, zz));
-            zv[TS * K + lane] = z0; zv[TS * K + lane + 32] = z1;
-            cz[lane] = z0; cz[lane + 32] = z1;
-            __syncwarp();
+            chain_bar();
+            zz += tile_matvec_rows(W, crhs, zv + TS * K, cz, cw);
+            chain_bar();
             if (a.mode >= DAG_FIT) {      // alpha_K starts as W_KK^T z_K; the bulk stream adds W_IK^T z_I, I > K
                 double a0, a1;
-                tile_matvec_t_warp(W, cz, a0, a1);
-                alv[TS * K + lane] = a0; alv[TS * K + lane + 32] = a1;
+                tile_matvec_t_rows(W, cz, a0, a1, cw);
+                cpart[cw * TS + lane] = a0; cpart[cw * TS + lane + 32] = a1;
+                chain_bar();
+                if (cw == 0) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int c = lane + 32 * half;
+                        alv[TS * K + c] = (cpart[c] + cpart[TS + c]) + (cpart[2 * TS + c] + cpart[3 * TS + c]);
+                    }
+                }
             }
-            fence_proxy_async();          // W (and, in FACTOR mode, L) may be written through by a bulk store
-            __syncwarp();
-            if (lane == 0) sync_arrive(&sync[1]);
+            chain_bar();
+            if (cw == 0 && lane == 0) sync_arrive(&sync[1]);      // event 2j + 2: z_K (and alpha_K) published
             PHEC(59);
         }
         PHEC(55);
         logdet = warp_sum(logdet);
         zz = warp_sum(zz);
-        if (lane == 0) {
+        if (lane == 0) { cpart[2 * cw] = logdet; cpart[2 * cw + 1] = zz; }
+        chain_bar();
+        if (cw == 0 && lane == 0) {
+            logdet = (cpart[0] + cpart[2]) + (cpart[4] + cpart[6]);
+            zz = (cpart[1] + cpart[3]) + (cpart[5] + cpart[7]);
             double ll = -0.5 * (N * kLog2Pi + 2.0 * logdet) - 0.5 * zz;
             if (first_fail != 0 || !isfinite(ll)) ll = -INFINITY;      // george: non-finite -> -inf (fabolas.py:58-66)
             a.ll[b] = ll;
@@ -268,26 +351,35 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     unsigned phases = 0u;                 // mbarrier phase parity per slot (uniform)
     double acc[4][2][2];
     acc_zero(acc);
-    double gacc[MAX_PK + 1];              // [0] log_c0, [1..d] log_M_k, [MAX_D+1] log_gamma2, [MAX_D+2] log_cb, [MAX_PK] yerr2
-#pragma unroll
-    for (int k = 0; k <= MAX_PK; ++k) gacc[k] = 0.0;
+    double* gsum_w = red + w * (MAX_PK + 1);   // this warp's gradient partial sums (contract_acc)
+    if (lane <= MAX_PK) gsum_w[lane] = 0.0;
     int cur_r = -1, cur_c = -1;           // tile rows whose coordinate slices are staged (slice mode)
 
     PHB(40);
+    // the head of the next op record (12 ints, L2 latency) is fetched while the current op executes
+    const int4* nxp = reinterpret_cast<const int4*>(a.bulk);
+    int4 n0 = __ldg(nxp), n1 = __ldg(nxp + 1), n2 = __ldg(nxp + 2);
     for (int i = 0; i < a.nbulk; ++i) {
         PHB(41);
         const DagOp* op = a.bulk + i;
-        const int type = __ldg(&op->type), I = __ldg(&op->I), J = __ldg(&op->J), k = __ldg(&op->k);
-        const int sA = __ldg(&op->slotA), sB = __ldg(&op->slotB), sC = __ldg(&op->slotC);
-        const int wo = __ldg(&op->wait_other), wait_mask = __ldg(&op->wait_mask), flags = __ldg(&op->flags);
+        const int type = n0.x, I = n0.y, J = n0.z, k = n0.w;
+        const int sA = n1.x, sB = n1.y, sC = n1.z;
+        const int wo = n1.w, wait_mask = n2.x, flags = n2.y, st_slot = n2.z, st_tile = n2.w;
         if (tid == 0 && (flags & DOPF_WAIT_READ)) bulk_s2g_wait_read();
         named_bar_sync(1, DAG_BULK_THREADS);          // every bulk warp is done with the previous operation
+        if (i + 1 < a.nbulk) {
+            nxp = reinterpret_cast<const int4*>(a.bulk + i + 1);
+            n0 = __ldg(nxp); n1 = __ldg(nxp + 1); n2 = __ldg(nxp + 2);
+        }
         if (wo > 0) {
-            if (lane == 0) spin_until(&sync[1], wo);
+            // chain op c publishes two events: 2c + 1 (tiles final) and 2c + 2 (vectors); a panel solve that only
+            // waits for its own diagonal tile starts on the first and takes z before its epilogue
+            const int need = (type == DOP_TRSM && wo == J + 1) ? 2 * wo - 1 : 2 * wo;
+            if (lane == 0) spin_until(&sync[1], need);
             __syncwarp();
         }
         if (tid == 0) {
-            const int nload = __ldg(&op->nload), st_slot = __ldg(&op->st_slot);
+            const int nload = __ldg(&op->nload);
             if (flags & DOPF_DRAIN) bulk_s2g_wait_all();
             if (nload > 0) fence_proxy_async();
             for (int l = 0; l < nload; ++l) {
@@ -295,7 +387,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
                 bulk_g2s(slots + (size_t)ls * TILE_ELEMS, ws_tile(lt), TILE_BYTES, &bars[ls]);
             }
             if (st_slot >= 0)
-                bulk_s2g(ws_tile(__ldg(&op->st_tile)), slots + (size_t)st_slot * TILE_ELEMS, TILE_BYTES);
+                bulk_s2g(ws_tile(st_tile), slots + (size_t)st_slot * TILE_ELEMS, TILE_BYTES);
         }
         PHE(41);
         PHB(42);
@@ -313,8 +405,8 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
         if (type == DOP_BUILD || (type == DOP_P2_MMA && (flags & DOPF_LAST))) {
             if (!a.resident) {            // slice mode: stage the coordinates (and alpha) of the two tile rows
                 bool staged = false;
-                if (cur_r != I) { stage_slice(sl_r, gd, h, I); cur_r = I; staged = true; }
-                if (cur_c != J) { stage_slice(sl_c, gd, h, J); cur_c = J; staged = true; }
+                if (cur_r != I) { stage_slice(sl_r, gd, hfull, I); cur_r = I; staged = true; }
+                if (cur_c != J) { stage_slice(sl_c, gd, hfull, J); cur_c = J; staged = true; }
                 if (type == DOP_P2_MMA) {
                     if (tid < TS) al_r[tid] = alv[TS * I + tid];
                     else if (tid < 2 * TS) al_c[tid - TS] = alv[TS * J + tid - TS];
@@ -351,6 +443,8 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             double r2[4][2][2];
             acc_zero(r2);
             tile_mma<false, true, false>(r2, C, Bt, wt, 0, wt.n0 + 16);
+            if (lane == 0) spin_until(&sync[1], 2 * J + 2);
+            __syncwarp();
             const double* zJ = zv + TS * J;
             double zc0[2], zc1[2];
 #pragma unroll
@@ -412,7 +506,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
                 PHB(50);
                 const double* ar_p = a.resident ? alv + TS * I : al_r;
                 const double* ac_p = a.resident ? alv + TS * J : al_c;
-#define FAB_CONTRACT_CASE(DD) case DD: contract_tile<DD>(acc, gacc, zr_p, zc_p, ur_p, uc_p, ar_p, ac_p, ldz, h, N, gd.family, I, J, wt, etab); break;
+#define FAB_CONTRACT_CASE(DD) case DD: contract_acc<DD>(acc, gsum_w, zr_p, zc_p, ur_p, uc_p, ar_p, ac_p, ldz, h, N, gd.family, I, J, wt, etab); break;
                 switch (d) {
                     FAB_CONTRACT_CASE(1) FAB_CONTRACT_CASE(2) FAB_CONTRACT_CASE(3) FAB_CONTRACT_CASE(4)
                     FAB_CONTRACT_CASE(5) FAB_CONTRACT_CASE(6) FAB_CONTRACT_CASE(7) FAB_CONTRACT_CASE(8)
@@ -430,14 +524,19 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     PHB(51);
 
     // the chain has published the log-likelihood, the failure flag and its share of alpha
-    if (lane == 0) spin_until(&sync[1], a.nchain + 1);
+    if (lane == 0) spin_until(&sync[1], 2 * a.nchain + 1);
     __syncwarp();
     named_bar_sync(1, DAG_BULK_THREADS);
     if (a.mode == DAG_FIT && a.resident)
         for (int i = tid; i < Np; i += DAG_BULK_THREADS) a.wk.alpha[(size_t)b * Np + i] = alv[i];
     if (a.mode == DAG_GRAD && a.grad) {
-        bulk_sum<MAX_PK + 1>(gacc, red);
         if (tid == 0) {
+            double gacc[MAX_PK + 1];
+            for (int q = 0; q <= MAX_PK; ++q) {
+                double sgm = 0.0;
+                for (int ww = 0; ww < NWARPS; ++ww) sgm += red[ww * (MAX_PK + 1) + q];
+                gacc[q] = sgm;
+            }
             double* go = a.grad + (size_t)b * (Pk + 1);
             const bool bad = sync[2] != 0;             // not positive definite: no factor to differentiate
             go[0] = bad ? NAN : 0.5 * gacc[0];

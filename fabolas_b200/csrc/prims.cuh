@@ -170,6 +170,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 #endif
 }
 
+// Producer side of a named barrier: counts this thread in without waiting (pairs with named_bar_sync on
+// the consumer side; `nthreads` = arriving + waiting threads).
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+#ifdef FAB_CUSIM
+    cusim_named_barrier_arrive(id, nthreads);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ struct dim3 {
 struct double2 { double x, y; };
 struct double4 { double x, y, z, w; };
 struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace cusim {
@@ -278,15 +279,21 @@ static inline int __syncthreads_or(int pred) {
     CUSIM_RESTORE_TID();
     return r;
 }
-// named barrier (PTX bar.sync id, nthreads): rendezvous of exactly `count` threads of the block
+// named barrier (PTX bar.sync / bar.arrive id, nthreads): completes when `count` threads of the block have
+// arrived (bar.arrive counts a thread in without waiting)
+namespace cusim { struct NamedBar { int arrived[16]; unsigned long long gen[16]; }; inline NamedBar& NB() { static NamedBar b{}; return b; } }
 static inline void cusim_named_barrier(int id, int count) {
-    static int arrived[16];
-    static unsigned long long gen[16];
-    const unsigned long long g = gen[id];
-    ++arrived[id];
-    while (gen[id] == g) {
-        if (arrived[id] >= count) { arrived[id] = 0; ++gen[id]; break; }
+    cusim::NamedBar& b = cusim::NB();
+    const unsigned long long g = b.gen[id];
+    ++b.arrived[id];
+    while (b.gen[id] == g) {
+        if (b.arrived[id] >= count) { b.arrived[id] = 0; ++b.gen[id]; break; }
         cusim::yield();
     }
     CUSIM_RESTORE_TID();
+}
+static inline void cusim_named_barrier_arrive(int id, int count) {
+    cusim::NamedBar& b = cusim::NB();
+    ++b.arrived[id];
+    if (b.arrived[id] >= count) { b.arrived[id] = 0; ++b.gen[id]; }
 }
