@@ -47,6 +47,7 @@ SIGNATURES = {
     "fab_ctx_debug_set_max_slots": (_c_int, [_vp, _c_int]),
     "fab_ctx_debug_force_slices": (_c_int, [_vp, _c_int]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
+    "fab_debug_dag_verify": (_c_int, [_c_int, _c_int, _c_int, ctypes.c_char_p, _c_int, ctypes.POINTER(_c_int)]),
 }
 
 

@@ -1,7 +1,5 @@
 // api.cu -- C ABI (include/fabolas_b200.h): context, workspaces, launch logic.
 #include "../../include/fabolas_b200.h"
-#include "gp_factor.cuh"
-#include "gp_grad.cuh"
 #include "gp_dag.cuh"
 #include "gp_predict.cuh"
 #include "epmgp.cuh"
@@ -9,7 +7,6 @@
 #include "kmat.cuh"
 
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -29,7 +26,7 @@ struct fab_ctx {
     double* dy = nullptr; size_t capy = 0;
     // workspaces
     GpWork wk{};
-    size_t capL = 0, capD = 0, capZ = 0, capA = 0, capW = 0;
+    size_t capL = 0, capZ = 0, capA = 0, capW = 0;
     double* dTheta = nullptr; size_t capT = 0;   // hyper-parameters of the resident models
     double* dYerr2 = nullptr; size_t capY = 0;
     int* dInfo = nullptr; size_t capI = 0;
@@ -44,15 +41,10 @@ struct fab_ctx {
     int wsB = 0;            // walkers the factor workspace currently describes
     bool factored = false;
     bool inverted = false;  // workspace holds W = L^-1 (and alpha) instead of L
-    // cached device copies of the static tile programs: [0] fit (phase 1 only), [1] gradient
-    TileOp* dProg[2] = {nullptr, nullptr};
-    int progN[2] = {0, 0}, progNT[2] = {-1, -1}, progSlots[2] = {-1, -1};
-    std::vector<TileOp> hProg[2];
     // fused warp-specialised kernel (gp_dag.cuh): cached static programs per (NT, slots, mode)
     struct DagDev { DagOp* bulk = nullptr; DagOp* chain = nullptr; int nbulk = 0, nchain = 0; DagProgram host; };
     std::map<long long, DagDev> dag;
     double* wkSpill = nullptr; size_t capSpill = 0;
-    bool legacy = false;         // FAB_LEGACY=1: the two-kernel path (gp_factor_kernel + gp_grad_kernel)
     int smem_optin = 232448;
     int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
     int force_slices = 0;        // test knob: never keep all coordinates resident in the gradient kernel
@@ -122,8 +114,6 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess && v > 0)
         c->smem_optin = v;
-    cudaFuncSetAttribute(gp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-    cudaFuncSetAttribute(gp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(gp_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(gp_predict_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(epmgp_ep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -131,8 +121,6 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
     cudaFuncSetAttribute(es_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(gp_predict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
 #endif
-    const char* lg = getenv("FAB_LEGACY");
-    c->legacy = lg && lg[0] == '1';
     *out = c;
     return FAB_OK;
 }
@@ -150,7 +138,7 @@ int fab_ctx_destroy(fab_ctx* c) {
 #endif
     for (auto& kv : c->dag) { cudaFree(kv.second.bulk); cudaFree(kv.second.chain); }
     cudaFree(c->wkSpill);
-    cudaFree(c->wk.Lw); cudaFree(c->wk.Dinv); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw); cudaFree(c->dProg[0]); cudaFree(c->dProg[1]);
+    cudaFree(c->wk.Lw); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw);
     delete c;
     return FAB_OK;
 }
@@ -159,6 +147,19 @@ int fab_ctx_debug_set_max_slots(fab_ctx* c, int n) {
     if (!c || n < 4 || n > MAX_SLOTS) return FAB_EINVAL;
     c->max_slots = n;
     return FAB_OK;
+}
+
+int fab_debug_dag_verify(int NT, int nslot, int mode, char* msg, int msg_len, int* stats) {
+    if (mode < DAG_LL || mode > DAG_GRAD) return FAB_EINVAL;
+    const DagProgram P = build_dag_program(NT, nslot, mode);
+    const std::string e = dag_verify(P);
+    if (msg && msg_len > 0) { strncpy(msg, e.c_str(), msg_len - 1); msg[msg_len - 1] = 0; }
+    if (stats) {
+        int nl = 0, ns = 0;
+        for (const DagOp& d : P.bulk) { nl += d.nload; ns += d.st_slot >= 0; }
+        stats[0] = (int)P.bulk.size(); stats[1] = (int)P.chain.size(); stats[2] = nl; stats[3] = ns;
+    }
+    return e.empty() ? 0 : -1;
 }
 
 int fab_ctx_debug_force_slices(fab_ctx* c, int on) {
@@ -218,69 +219,6 @@ int fab_gp_set_data(fab_ctx* c, int family, const double* X, int N, int D, const
     return FAB_OK;
 }
 
-static int launch_factor(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info,
-                         bool store) {
-    const GpData& gd = c->gd;
-    const int ntiles = gd.NT * (gd.NT + 1) / 2;
-    // slots: everything if it fits, else as many as shared memory allows (>= 4 needed)
-    int nslot = ntiles < c->max_slots ? ntiles : c->max_slots;
-    while (nslot > 0 && factor_smem_bytes(nslot, gd.d) > (size_t)c->smem_optin) --nslot;
-    const bool fits = nslot >= ntiles;
-    if (nslot < 4 && !fits) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA factor kernel");
-    const bool need_ws = store || !fits;
-    int rc;
-    if ((rc = ensure(c, &c->wk.accw, &c->capW, (size_t)B * gd.Np)) != FAB_OK) return rc;
-    if (need_ws) {
-        if ((rc = ensure(c, &c->wk.Lw, &c->capL, (size_t)B * ntiles * TILE_ELEMS)) != FAB_OK) return rc;
-        if ((rc = ensure(c, &c->wk.Dinv, &c->capD, (size_t)B * gd.NT * 512)) != FAB_OK) return rc;
-        if ((rc = ensure(c, &c->wk.zvec, &c->capZ, (size_t)B * gd.Np)) != FAB_OK) return rc;
-        if ((rc = ensure(c, &c->wk.alpha, &c->capA, (size_t)B * gd.Np)) != FAB_OK) return rc;
-    }
-    FactorArgs a;
-    a.gd = gd; a.wk = c->wk;
-    if (!need_ws) { a.wk.Lw = nullptr; a.wk.Dinv = nullptr; a.wk.zvec = nullptr; }
-    a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info;
-    a.nslot = nslot; a.store = need_ws ? 1 : 0;
-    const size_t smem = factor_smem_bytes(nslot, gd.d);
-    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
-    FAB_LAUNCH(gp_factor_kernel, B, NTHREADS, smem, c->stream, a);
-    FAB_CUDA(c, cudaGetLastError());
-    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
-    c->resident = false;
-    c->es_ready = false;
-    if (need_ws) { c->wsB = B; c->factored = true; c->inverted = false; }
-    return FAB_OK;
-}
-
-// W = L^-1 in place + alpha (+ gradient when grad != null); needs the workspace of launch_factor(store).
-static int launch_grad(fab_ctx* c, const double* theta, const double* yerr2, int B, double* grad, const int* info) {
-    const GpData& gd = c->gd;
-    int nslot = c->max_slots;
-    // coordinates + alpha of all rows resident in shared memory when that costs no tile slot
-    int resident = (!c->force_slices && grad_smem_bytes(nslot, gd.d, gd.Np) <= (size_t)c->smem_optin) ? 1 : 0;
-    while (nslot > 0 && grad_smem_bytes(nslot, gd.d, resident ? gd.Np : 0) > (size_t)c->smem_optin) --nslot;
-    if (nslot < 3) return fail(c, FAB_EUNSUPPORTED, "not enough shared memory for the gradient kernel");
-    const int which = grad ? 1 : 0;
-    if (c->progNT[which] != gd.NT || c->progSlots[which] != nslot) {
-        c->hProg[which] = build_grad_program(gd.NT, nslot, grad != nullptr);   // host vector stays alive: async copy source
-        const size_t n = c->hProg[which].size();
-        if (c->dProg[which]) { cudaFree(c->dProg[which]); c->dProg[which] = nullptr; }
-        if (cudaMalloc(reinterpret_cast<void**>(&c->dProg[which]), n * sizeof(TileOp)) != cudaSuccess)
-            return fail(c, FAB_ENOMEM, "tile program allocation failed");
-        FAB_CUDA(c, cudaMemcpyAsync(c->dProg[which], c->hProg[which].data(), n * sizeof(TileOp), cudaMemcpyHostToDevice,
-                                    c->stream));
-        c->progN[which] = (int)n; c->progNT[which] = gd.NT; c->progSlots[which] = nslot;
-    }
-    GradArgs a;
-    a.gd = gd; a.wk = c->wk; a.theta = theta; a.yerr2 = yerr2; a.grad = grad; a.info = info; a.nslot = nslot;
-    a.prog = c->dProg[which]; a.nops = c->progN[which]; a.resident = resident;
-    FAB_LAUNCH(gp_grad_kernel, B, NTHREADS, grad_smem_bytes(nslot, gd.d, resident ? gd.Np : 0), c->stream, a);
-    FAB_CUDA(c, cudaGetLastError());
-    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[2], c->stream)); c->ev_used = 2; }
-    c->inverted = true;
-    return FAB_OK;
-}
-
 // One launch of the fused kernel.  mode: DAG_LL (ll only), DAG_FACTOR (+ L tiles in the workspace),
 // DAG_FIT (+ W = L^-1 tiles and alpha in the workspace), DAG_GRAD (+ gradient).
 static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info, double* grad,
@@ -336,11 +274,7 @@ int fab_gp_loglik_batch(fab_ctx* c, const double* theta, const double* yerr2, in
     if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
     if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    if (!c->legacy) return launch_dag(c, theta, yerr2, B, ll, info, grad, grad ? DAG_GRAD : DAG_LL);
-    int rc = launch_factor(c, theta, yerr2, B, ll, info, grad != nullptr);
-    if (rc != FAB_OK) return rc;
-    if (grad) return launch_grad(c, theta, yerr2, B, grad, info);
-    return FAB_OK;
+    return launch_dag(c, theta, yerr2, B, ll, info, grad, grad ? DAG_GRAD : DAG_LL);
 }
 
 int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info) {
@@ -348,10 +282,7 @@ int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2,
     if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
     if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    if (!c->legacy) return launch_dag(c, theta, yerr2, B, ll, info, nullptr, DAG_FACTOR);
-    int rc = launch_factor(c, theta, yerr2, B, ll, info, true);
-    if (rc != FAB_OK) return rc;
-    return FAB_OK;
+    return launch_dag(c, theta, yerr2, B, ll, info, nullptr, DAG_FACTOR);
 }
 
 // factorize + W = L^-1 + alpha, hyper-parameters copied into the context: models become resident.
@@ -360,8 +291,7 @@ int fab_gp_fit_batch(fab_ctx* c, const double* theta, const double* yerr2, int B
     if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
     if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    int rc = c->legacy ? fab_gp_factorize_batch(c, theta, yerr2, B, ll, info)
-                       : launch_dag(c, theta, yerr2, B, ll, info, nullptr, DAG_FIT);
+    int rc = launch_dag(c, theta, yerr2, B, ll, info, nullptr, DAG_FIT);
     if (rc != FAB_OK) return rc;
     const GpData& gd = c->gd;
     if ((rc = ensure(c, &c->dTheta, &c->capT, (size_t)B * gd.Pk)) != FAB_OK) return rc;
@@ -370,10 +300,6 @@ int fab_gp_fit_batch(fab_ctx* c, const double* theta, const double* yerr2, int B
     FAB_CUDA(c, cudaMemcpyAsync(c->dTheta, theta, sizeof(double) * B * gd.Pk, cudaMemcpyDeviceToDevice, c->stream));
     FAB_CUDA(c, cudaMemcpyAsync(c->dYerr2, yerr2, sizeof(double) * B, cudaMemcpyDeviceToDevice, c->stream));
     FAB_CUDA(c, cudaMemcpyAsync(c->dInfo, info, sizeof(int) * B, cudaMemcpyDeviceToDevice, c->stream));
-    if (c->legacy) {
-        rc = launch_grad(c, c->dTheta, c->dYerr2, B, nullptr, c->dInfo);
-        if (rc != FAB_OK) return rc;
-    }
     c->resident = true;
     return FAB_OK;
 }

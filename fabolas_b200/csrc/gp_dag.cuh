@@ -13,7 +13,6 @@
 // The covariance matrix and its inverse are never materialised.
 #pragma once
 #include "gp_common.cuh"
-#include "gp_grad.cuh"
 #include "chain_ops.cuh"
 #include "dag_program.h"
 

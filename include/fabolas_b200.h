@@ -133,11 +133,18 @@ int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta
                       int Na, const double* Xb, int Nb, int D, double amp_mult, double* K, double* dK);
 
 /* Debug / test knob: cap the number of shared-memory tile slots (4..6) so that small problems
- * exercise the L2/HBM tile-streaming path of the factor and gradient kernels.                     */
+ * exercise the L2/HBM tile-streaming path of the fused GP kernel.                                  */
 int fab_ctx_debug_set_max_slots(fab_ctx* ctx, int n);
-/* Debug / test knob: make the gradient kernel stage 64-row coordinate slices per tile pair (its
- * large-N mode) even when all coordinates would fit in shared memory.                              */
+/* Debug / test knob: make the fused GP kernel stage 64-row coordinate slices per tile (its large-N
+ * mode) even when all coordinates would fit in shared memory.                                      */
 int fab_ctx_debug_force_slices(fab_ctx* ctx, int on);
+/* Debug / test access to the host-side static scheduler of the fused GP kernel (no device needed):
+ * builds the two-stream tile program for NT tile rows, `nslot` shared-memory slots and `mode`
+ * (0 log-likelihood, 1 + factor tiles stored, 2 fit, 3 gradient) and runs the independent verifier
+ * (slot contents at every access, every cross-stream hazard ordered by an explicit wait).
+ * Returns 0 when the program is valid; otherwise -1 and the reason in msg.  stats (may be NULL)
+ * receives {bulk ops, chain ops, tile loads, tile stores}.                                           */
+int fab_debug_dag_verify(int NT, int nslot, int mode, char* msg, int msg_len, int* stats);
 
 /* Debug / test access: copy the dense lower Cholesky factor of walker b (N x N row-major, device)
  * out of the tiled workspace left by the last fab_gp_loglik_batch(grad != NULL) / factorize call. */
