@@ -31,8 +31,9 @@ sys.path.insert(0, ROOT)
 METRIC = "GP loglik+grad evals/sec (N=256, 128 walkers/GPU)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one gp_dag_kernel launch from the committed ncu --set full
 # capture (profiles/); None until a capture of the current kernel exists.
-TRAFFIC_BYTES_PER_LAUNCH = None
-TRAFFIC_SOURCE = None
+TRAFFIC_BYTES_PER_LAUNCH = 167424 + 2158080
+TRAFFIC_SOURCE = ("profiles/r01m_ncu_full_raw.csv: dram__bytes_read.sum 167 KB + dram__bytes_write.sum 2.16 MB per "
+                  "launch of 128 evals (algorithmic bytes 128 x 14.4 KB = 1.84 MB; tiles stream through L2 only)")
 UNIT = "evals/s"
 CONFIG_ID = 2
 
@@ -180,23 +181,25 @@ def run_ours(args):
     theta_h = torch.from_numpy(w["theta"][rank * Bg:(rank + 1) * Bg].copy()).pin_memory()
     yerr2_h = torch.from_numpy(w["yerr2"][rank * Bg:(rank + 1) * Bg].copy()).pin_memory()
     theta_d, yerr2_d = theta_h.cuda(), yerr2_h.cuda()
-    ll_all = torch.empty(world * Bg, dtype=torch.float64, device="cuda")
-    g_all = torch.empty(world * Bg, P, dtype=torch.float64, device="cuda")
+    # results of one rank packed as [grad (Bg x P) | ll (Bg)] so that ONE all-gather ships both
+    packed = torch.empty(Bg * P + Bg, dtype=torch.float64, device="cuda")
+    g_loc, ll_loc = packed[:Bg * P].view(Bg, P), packed[Bg * P:]
+    info_loc = torch.empty(Bg, dtype=torch.int32, device="cuda")
+    packed_all = torch.empty(world * (Bg * P + Bg), dtype=torch.float64, device="cuda")
     ll_host = torch.empty(Bg, dtype=torch.float64).pin_memory()
     g_host = torch.empty(Bg, P, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # 256 MB > 126 MB L2
 
     def step_resident():
-        ll, g, info = eng.loglik(theta_d, yerr2_d, grad=True)
+        ll, g, info = eng.loglik(theta_d, yerr2_d, grad=True, out=(ll_loc, g_loc, info_loc))
         if world > 1:
-            dist.all_gather_into_tensor(ll_all, ll)
-            dist.all_gather_into_tensor(g_all, g)
+            dist.all_gather_into_tensor(packed_all, packed)
         return ll, g
 
     def step_e2e():
         th = theta_h.to("cuda", non_blocking=True)
         ye = yerr2_h.to("cuda", non_blocking=True)
-        ll, g, info = eng.loglik(th, ye, grad=True)
+        ll, g, info = eng.loglik(th, ye, grad=True, out=(ll_loc, g_loc, info_loc))
         ll_host.copy_(ll, non_blocking=True)
         g_host.copy_(g, non_blocking=True)
 
@@ -331,7 +334,7 @@ def run_ours(args):
             "config": {"workload": "BASELINE configs[1]: CNN-CIFAR10 space (5 hyper-parameters) + s, N=256, D=6, P=9, "
                                    "128 walkers per GPU, Matern52 x (linear+const) basis kernel",
                        "walkers_per_gpu": Bg, "N": N, "D": D, "l2_flush_between_steps": True,
-                       "parallelism": f"walkers sharded x{world}, NCCL all-gather of ll and grad"},
+                       "parallelism": f"walkers sharded x{world}, one NCCL all-gather of the packed (grad | ll) block per step"},
             "e2e": {"value": world * Bg / (ms_e2e / K * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(theta_h.numel() * 8 + yerr2_h.numel() * 8),
                     "d2h_bytes_per_step": int(ll_host.numel() * 8 + g_host.numel() * 8)},

@@ -173,12 +173,22 @@ class Engine:
             raise ValueError("one yerr2 per theta row")
         return theta, yerr2
 
-    def loglik(self, theta, yerr2, grad: bool = False):
+    def loglik(self, theta, yerr2, grad: bool = False, out=None):
+        """ll (B,), [grad (B, Pk + 1),] info (B,) of B hyper-parameter rows: one launch of the fused kernel.
+        `out` = (ll, grad or None, info): caller-owned contiguous result tensors (e.g. views of one packed
+        buffer that a single all-gather ships)."""
         theta, yerr2 = self._theta(theta, yerr2)
         B = theta.shape[0]
-        ll = self.empty(B)
-        info = self.empty(B, dtype=torch.int32)
-        g = self.empty(B, self.Pk + 1) if grad else None
+        if out is not None:
+            ll, g, info = out
+            if ll.numel() != B or info.numel() != B or (grad and (g is None or g.numel() != B * (self.Pk + 1))):
+                raise ValueError("out tensors do not match the batch")
+            if not (ll.is_contiguous() and info.is_contiguous() and (g is None or g.is_contiguous())):
+                raise ValueError("out tensors must be contiguous")
+        else:
+            ll = self.empty(B)
+            info = self.empty(B, dtype=torch.int32)
+            g = self.empty(B, self.Pk + 1) if grad else None
         self._check(self.lib.fab_gp_loglik_batch(self._ctx, _ptr(theta), _ptr(yerr2), B, _ptr(ll), _ptr(g),
                                                  _ptr(info)), "fab_gp_loglik_batch")
         return (ll, g, info) if grad else (ll, info)

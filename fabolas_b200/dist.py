@@ -56,7 +56,13 @@ def sharded_loglik(engine, theta, yerr2, grad: bool = False):
     else:
         out = (engine.empty(0), engine.empty(0, engine.Pk + 1), engine.empty(0, dtype=torch.int32)) if grad else \
               (engine.empty(0), engine.empty(0, dtype=torch.int32))
-    return tuple(_allgather_rows(t, B) for t in out)
+    if size == 1:
+        return out
+    # one collective per step: rows packed as [ll | grad | info] (info is a small integer, exact in FP64)
+    cols = [out[0][:, None]] + ([out[1]] if grad else []) + [out[-1].double()[:, None]]
+    packed = _allgather_rows(torch.cat(cols, 1), B)
+    ll, info = packed[:, 0].contiguous(), packed[:, -1].to(torch.int32)
+    return (ll, packed[:, 1:-1].contiguous(), info) if grad else (ll, info)
 
 
 def sharded_argmax(values: torch.Tensor, offset: int):
