@@ -478,6 +478,16 @@ extern "C" int fab_debug_phase_reset(void) {
     long long z[64] = {0};
     return cudaMemcpyToSymbol(fab::g_phase, z, sizeof(z)) == cudaSuccess ? 0 : -1;
 }
+extern "C" int fab_debug_trace_read(long long* out) {      // [2][128][4] clock64 stamps of CTA 0 (bulk ops, chain ops)
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, fab::g_trace, sizeof(long long) * 2 * 128 * 4) == cudaSuccess ? 0 : -1;
+}
+extern "C" int fab_debug_program_read(int NT, int nslot, int mode, int* out, int max_ops) {   // (type, I, J, k) per bulk op
+    const DagProgram P = build_dag_program(NT, nslot, mode);
+    int n = 0;
+    for (const DagOp& d : P.bulk) { if (n >= max_ops) break; out[4 * n] = d.type; out[4 * n + 1] = d.I; out[4 * n + 2] = d.J; out[4 * n + 3] = d.k; ++n; }
+    return n;
+}
 extern "C" int fab_debug_phase_read(long long* out) {
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(out, fab::g_phase, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;

@@ -30,18 +30,20 @@ enum DagOpType {
     DOP_NOP = 0,
     DOP_BUILD = 1,     // acc = K(I,J) entries (registers)
     DOP_MMA_NT = 2,    // acc -= A * B^T                 A = L(I,k), B = L(J,k)
-    DOP_PUT = 3,       // slot C = acc                   unfinished tile U(I,J)
+    DOP_PUT = 3,       // slot C = acc                   k = kind of the tile put: unfinished U(I,J), partial P / T
     DOP_TRSM = 4,      // C = C * B^T                    B = W(J,J);  accw_I += C z_J     -> L(I,J)
     DOP_P1_MMA = 5,    // acc (+)= A * B                 A = L(I,k), B = W(k,J)
-    DOP_P1_FIN = 6,    // C = -A * acc                   A = W(I,I);  alpha_J += C^T z_I   -> W(I,J)
+    DOP_P1_FIN = 6,    // C = -A * C                     A = W(I,I), C = T(I,J);  alpha_J += C^T z_I   -> W(I,J)
     DOP_P2_MMA = 7,    // acc (+)= A^T * B               A = W(k,I), B = W(k,J); LAST: contraction with dK
-    DOP_CH_POTRF = 8   // chain: slot A: U(K,K) -> L(K,K) in place; slot C = W(K,K); z_K, log det, alpha_K
+    DOP_CH_POTRF = 8,  // chain: slot A: U(K,K) -> L(K,K) in place; slot C = W(K,K); z_K, log det, alpha_K
+    DOP_GET = 9        // acc = slot C                   partial tile P(I,J) picked up again
 };
 enum DagOpFlags {
     DOPF_FIRST = 1,       // first product of an accumulation: acc = 0
     DOPF_LAST = 2,        // last product of a K^-1 tile: contraction
     DOPF_WAIT_READ = 4,   // a slot that is the source of an earlier bulk store is overwritten from here on
-    DOPF_DRAIN = 8        // a tile loaded here was stored since the last drain: wait for all bulk stores first
+    DOPF_DRAIN = 8,       // a tile loaded here was stored since the last drain: wait for all bulk stores first
+    DOPF_INPLACE = 16     // PUT over the partial tile P(I,J) that the preceding GET picked up (same slot)
 };
 constexpr int DAG_MAX_LOADS = 6;
 constexpr int DAG_PREFETCH_DEPTH = 3;
@@ -71,7 +73,10 @@ struct DagProgram {
 
 namespace dagdetail {
 
-enum { TK_L = 0, TK_W = 1, TK_U = 2 };
+// L, W: final tiles (have a workspace location); U: updated covariance tile awaiting its chain op / panel
+// solve; P: partially updated diagonal tile; T: sum_k L(I,k) W(k,J) awaiting W(I,I).  U, P, T never leave
+// shared memory (pinned).
+enum { TK_L = 0, TK_W = 1, TK_U = 2, TK_P = 3, TK_T = 4 };
 inline int tid_of(int kind, int I, int J) { return (kind << 28) | (I << 14) | J; }
 inline int tid_kind(int id) { return id >> 28; }
 inline int tid_I(int id) { return (id >> 14) & 0x3fff; }
@@ -84,7 +89,7 @@ inline int ws_index(int id, int mode, int NT) {
     return tri(tid_I(id), tid_J(id));
 }
 
-enum { T_FA = 0, T_CH = 1, T_FB = 2, T_P1 = 3, T_P2 = 4 };
+enum { T_FA = 0, T_CH = 1, T_FB = 2, T_P1 = 3, T_P2 = 4, T_FA1 = 5, T_FA2 = 6, T_P1A = 7, T_P1B = 8 };
 struct Task {
     int kind, I, J;
     std::vector<int> deps, succ;
@@ -92,8 +97,8 @@ struct Task {
     bool scheduled = false;
 };
 // estimated costs in microseconds (B200, profiles/r01f_phase_cycles.txt)
-constexpr double C_BUILD = 1.2, C_MMA = 2.4, C_PUT = 0.3, C_TRSM = 2.2, C_P1FIN = 2.6, C_CONTRACT = 1.8,
-                 C_CHAIN = 9.5;
+constexpr double C_BUILD = 2.7, C_MMA = 2.3, C_PUT = 0.3, C_TRSM = 3.2, C_P1FIN = 2.7, C_CONTRACT = 3.8,
+                 C_CHAIN = 21.0;
 
 struct SymOp {            // one op before slot assignment
     int stream;           // 0 bulk, 1 chain
@@ -108,10 +113,18 @@ struct SymOp {            // one op before slot assignment
 
 }  // namespace dagdetail
 
-inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores = false);
+// split = true: tasks that would hold the accumulators across a wait for the chain are cut in two at a
+// PUT / GET boundary -- the diagonal tile's build and early updates run before the panel solve it still needs
+// (FA1 | FA2), the products of an inverse tile run before its diagonal inverse exists (P1A | P1B).
+inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_stores, bool split);
+inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores = false) {
+    DagProgram P = build_dag_program_impl(NT, nslot, mode, all_stores, true);
+    if (!P.ok) P = build_dag_program_impl(NT, nslot, mode, all_stores, false);   // fewer pinned tiles
+    return P;
+}
 
 // -------------------------------------------------------------------------------------------------
-inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores) {
+inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_stores, bool split) {
     using namespace dagdetail;
     DagProgram P;
     P.NT = NT; P.nslot = nslot; P.mode = mode;
@@ -129,35 +142,57 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
     };
     auto id = [&](int kind, int I, int J) { return key.at(K3(kind, I, J)); };
     for (int K = 0; K < NT; ++K) {
-        for (int I = K; I < NT; ++I) add(T_FA, I, K, C_BUILD + C_MMA * K + C_PUT);
+        for (int I = K; I < NT; ++I) {
+            if (split && I == K && K >= 1) {
+                add(T_FA1, K, K, C_BUILD + C_MMA * (K - 1) + C_PUT);
+                add(T_FA2, K, K, C_PUT + C_MMA + C_PUT);
+            } else {
+                add(T_FA, I, K, C_BUILD + C_MMA * K + C_PUT);
+            }
+        }
         add(T_CH, K, K, C_CHAIN);
         for (int I = K + 1; I < NT; ++I) add(T_FB, I, K, C_TRSM);
     }
     if (with_p1)
         for (int I = 1; I < NT; ++I)
-            for (int J = 0; J < I; ++J) add(T_P1, I, J, C_MMA * (I - J) + C_P1FIN);
+            for (int J = 0; J < I; ++J) {
+                if (split) { add(T_P1A, I, J, C_MMA * (I - J) + C_PUT); add(T_P1B, I, J, C_P1FIN); }
+                else add(T_P1, I, J, C_MMA * (I - J) + C_P1FIN);
+            }
     if (with_p2)
         for (int J = 0; J < NT; ++J)
             for (int I = J; I < NT; ++I) add(T_P2, I, J, C_MMA * (NT - I) + C_CONTRACT);
     auto dep = [&](int t, int d) { T[t].deps.push_back(d); };
+    const bool dsplit = split;
+    auto fa_last = [&](int I, int K) { return (dsplit && I == K && K >= 1) ? id(T_FA2, K, K) : id(T_FA, I, K); };   // task that completes U(I,K)
+    auto p1_done = [&](int I, int J) { return split ? id(T_P1B, I, J) : id(T_P1, I, J); };                          // task that completes W(I,J)
     for (int K = 0; K < NT; ++K) {
         for (int I = K; I < NT; ++I) {
-            const int t = id(T_FA, I, K);
-            for (int J = 0; J < K; ++J) { dep(t, id(T_FB, I, J)); if (I != K) dep(t, id(T_FB, K, J)); }
+            if (dsplit && I == K && K >= 1) {
+                const int t1 = id(T_FA1, K, K), t2 = id(T_FA2, K, K);
+                for (int J = 0; J + 1 < K; ++J) dep(t1, id(T_FB, K, J));
+                dep(t2, t1); dep(t2, id(T_FB, K, K - 1));
+            } else {
+                const int t = id(T_FA, I, K);
+                for (int J = 0; J < K; ++J) { dep(t, id(T_FB, I, J)); if (I != K) dep(t, id(T_FB, K, J)); }
+            }
         }
-        dep(id(T_CH, K, K), id(T_FA, K, K));
+        dep(id(T_CH, K, K), fa_last(K, K));
         for (int I = K + 1; I < NT; ++I) { dep(id(T_FB, I, K), id(T_FA, I, K)); dep(id(T_FB, I, K), id(T_CH, K, K)); }
     }
     if (with_p1)
         for (int I = 1; I < NT; ++I)
             for (int J = 0; J < I; ++J) {
-                const int t = id(T_P1, I, J);
-                dep(t, id(T_CH, I, I)); dep(t, id(T_CH, J, J));
-                for (int k = J; k < I; ++k) dep(t, id(T_FB, I, k));
-                for (int k = J + 1; k < I; ++k) dep(t, id(T_P1, k, J));
+                // ta: the products sum_k L(I,k) W(k,J); tb: the multiplication by -W(I,I) (and the store of W(I,J))
+                const int ta = split ? id(T_P1A, I, J) : id(T_P1, I, J), tb = p1_done(I, J);
+                dep(tb, id(T_CH, I, I)); dep(ta, id(T_CH, J, J));
+                if (ta != tb) dep(tb, ta);
+                for (int k = J; k < I; ++k) dep(ta, id(T_FB, I, k));
+                for (int k = J + 1; k < I; ++k) dep(ta, p1_done(k, J));
                 // W(I,J) takes the place of L(I,J) in the workspace: every reader of L(I,J) comes first
-                for (int I2 = I + 1; I2 < NT; ++I2) dep(t, id(T_FA, I2, I));
-                if (J > 0) dep(t, id(T_P1, I, J - 1));
+                for (int I2 = I + 1; I2 < NT; ++I2) dep(tb, id(T_FA, I2, I));
+                for (int J2 = 0; J2 < J; ++J2) dep(tb, split ? id(T_P1A, I, J2) : id(T_P1, I, J2));
+                dep(tb, id(T_CH, I, I));
             }
     if (with_p2)
         for (int J = 0; J < NT; ++J)
@@ -165,8 +200,8 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
                 const int t = id(T_P2, I, J);
                 dep(t, id(T_CH, NT - 1, NT - 1));
                 dep(t, id(T_CH, I, I)); dep(t, id(T_CH, J, J));
-                for (int k = I + 1; k < NT; ++k) dep(t, id(T_P1, k, I));      // W(k,I), and alpha_I final
-                for (int k = J + 1; k < NT; ++k) dep(t, id(T_P1, k, J));      // W(k,J), and alpha_J final
+                for (int k = I + 1; k < NT; ++k) dep(t, p1_done(k, I));      // W(k,I), and alpha_I final
+                for (int k = J + 1; k < NT; ++k) dep(t, p1_done(k, J));      // W(k,J), and alpha_J final
             }
     const int nt = (int)T.size();
     for (int t = 0; t < nt; ++t) {
@@ -183,7 +218,15 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
 
     // ---- phase 1: list scheduling of the tasks on the two streams ----
     const int ucap = std::max(1, nslot - 3);       // unfinished (pinned, never stored) tiles alive at once
-    auto consumer_of_U = [&](int fa) { return T[fa].I == T[fa].J ? id(T_CH, T[fa].I, T[fa].I) : id(T_FB, T[fa].I, T[fa].J); };
+    // tasks that leave a pinned tile behind, and the task that consumes it
+    auto makes_pinned = [&](int t) { return T[t].kind == T_FA || T[t].kind == T_FA1 || T[t].kind == T_P1A; };
+    auto consumer_of = [&](int t) {
+        switch (T[t].kind) {
+        case T_FA1: return id(T_FA2, T[t].I, T[t].J);
+        case T_P1A: return id(T_P1B, T[t].I, T[t].J);
+        default: return T[t].I == T[t].J ? id(T_CH, T[t].I, T[t].I) : id(T_FB, T[t].I, T[t].J);
+        }
+    };
     double tfree[2] = {0.0, 0.0};
     std::vector<int> order[2];
     int remaining = nt;
@@ -199,12 +242,12 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
                 bool okd = true;
                 for (int d : T[t].deps) { if (!T[d].scheduled) { okd = false; break; } est = std::max(est, T[d].end); }
                 if (!okd) continue;
-                if (T[t].kind == T_FA) {               // cap on live unfinished tiles at the end of this task
+                if (makes_pinned(t)) {                 // cap on live pinned tiles at the end of this task
                     int unsched = 0;
                     std::vector<double> ends;
                     for (int f = 0; f < nt; ++f)
-                        if (T[f].kind == T_FA && T[f].scheduled) {
-                            const Task& c = T[consumer_of_U(f)];
+                        if (makes_pinned(f) && T[f].scheduled) {
+                            const Task& c = T[consumer_of(f)];
                             if (!c.scheduled) ++unsched; else if (c.end > est + T[t].cost) ends.push_back(c.end);
                         }
                     if (unsched >= ucap) continue;     // blocked until a consumer gets scheduled
@@ -247,7 +290,17 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
             case T_FA:
                 push(0, DOP_BUILD, I, J, 0, 0, -1, -1, -1, -1, -1, tm); tm += C_BUILD;
                 for (int k = 0; k < J; ++k) { push(0, DOP_MMA_NT, I, J, k, 0, tid_of(TK_L, I, k), tid_of(TK_L, J, k), -1, -1, -1, tm); tm += C_MMA; }
-                push(0, DOP_PUT, I, J, 0, 0, -1, -1, -1, -1, tid_of(TK_U, I, J), tm);
+                push(0, DOP_PUT, I, J, TK_U, 0, -1, -1, -1, -1, tid_of(TK_U, I, J), tm);
+                break;
+            case T_FA1:
+                push(0, DOP_BUILD, I, J, 0, 0, -1, -1, -1, -1, -1, tm); tm += C_BUILD;
+                for (int k = 0; k + 1 < J; ++k) { push(0, DOP_MMA_NT, I, J, k, 0, tid_of(TK_L, I, k), tid_of(TK_L, J, k), -1, -1, -1, tm); tm += C_MMA; }
+                push(0, DOP_PUT, I, J, TK_P, 0, -1, -1, -1, -1, tid_of(TK_P, I, J), tm);
+                break;
+            case T_FA2:
+                push(0, DOP_GET, I, J, TK_P, 0, tid_of(TK_P, I, J), -1, -1, -1, -1, tm); tm += C_PUT;
+                push(0, DOP_MMA_NT, I, J, J - 1, 0, tid_of(TK_L, I, J - 1), tid_of(TK_L, J, J - 1), -1, -1, -1, tm); tm += C_MMA;
+                push(0, DOP_PUT, I, J, TK_U, DOPF_INPLACE, -1, -1, tid_of(TK_P, I, J), tid_of(TK_U, I, J), -1, tm);
                 break;
             case T_CH:
                 push(1, DOP_CH_POTRF, I, I, I, 0, -1, -1, tid_of(TK_U, I, I), tid_of(TK_L, I, I), tid_of(TK_W, I, I), tm);
@@ -255,12 +308,16 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
             case T_FB:
                 push(0, DOP_TRSM, I, J, J, 0, tid_of(TK_W, J, J), -1, tid_of(TK_U, I, J), tid_of(TK_L, I, J), -1, tm);
                 break;
-            case T_P1:
+            case T_P1: case T_P1A:
                 for (int k = J; k < I; ++k) {
                     push(0, DOP_P1_MMA, I, J, k, k == J ? DOPF_FIRST : 0, tid_of(TK_L, I, k), tid_of(TK_W, k, J), -1, -1, -1, tm);
                     tm += C_MMA;
                 }
-                push(0, DOP_P1_FIN, I, J, I, 0, tid_of(TK_W, I, I), -1, -1, -1, tid_of(TK_W, I, J), tm);
+                push(0, DOP_PUT, I, J, TK_T, 0, -1, -1, -1, -1, tid_of(TK_T, I, J), tm); tm += C_PUT;
+                if (t.kind == T_P1) push(0, DOP_P1_FIN, I, J, I, 0, tid_of(TK_W, I, I), -1, tid_of(TK_T, I, J), tid_of(TK_W, I, J), -1, tm);
+                break;
+            case T_P1B:
+                push(0, DOP_P1_FIN, I, J, I, 0, tid_of(TK_W, I, I), -1, tid_of(TK_T, I, J), tid_of(TK_W, I, J), -1, tm);
                 break;
             case T_P2:
                 for (int k = I; k < NT; ++k) {
@@ -333,7 +390,7 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
         for (size_t i = 0; i < ops.size(); ++i)
             if (ops[i].stream == 1) { chain_pos_of_idx[ops[i].idx] = pos[i]; chain_end_t[ops[i].idx] = ops[i].t + C_CHAIN; }
         auto need_store = [&](int tile) {
-            if (tid_kind(tile) == TK_U) return false;
+            if (tid_kind(tile) >= TK_U) return false;           // U, P, T never leave shared memory
             if (tid_kind(tile) == TK_L && tid_I(tile) == tid_J(tile)) return mode == DAG_FACTOR;   // L(K,K) is dead after its chain op
             if (is_output(tile) || store_all) return true;
             auto it = reloaded_prev.find(tile);
@@ -433,9 +490,24 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
                 d.slotB = o.in[1] == o.in[0] ? d.slotA : resident(o.in[1]);
                 break;
             case DOP_PUT: {
+                if (o.inplace >= 0) {                       // over the partial tile the preceding GET picked up
+                    const int q = find(o.inplace);
+                    if (q < 0) { failed = true; P.err = "partial tile lost"; break; }
+                    touch(q);
+                    S[q].id = o.inplace_to; S[q].clean = false;
+                    d.slotC = q;
+                    break;
+                }
                 const int q = victim(false);
                 if (q < 0) { failed = true; P.err = "no slot for an unfinished tile"; break; }
                 overwrite(q, o.out, false);
+                d.slotC = q;
+                break;
+            }
+            case DOP_GET: {
+                const int q = find(o.in[0]);
+                if (q < 0) { failed = true; P.err = "partial tile lost"; break; }
+                touch(q);
                 d.slotC = q;
                 break;
             }
@@ -451,13 +523,14 @@ inline DagProgram build_dag_program(int NT, int nslot, int mode, bool all_stores
                 break;
             }
             case DOP_P1_FIN: {
+                const int q = find(o.inplace);
+                if (q < 0) { failed = true; P.err = "product tile lost"; break; }
+                touch(q);
+                d.slotC = q;
                 d.slotA = resident(o.in[0]);
                 if (failed) break;
-                const int q = victim(false);
-                if (q < 0) { failed = true; P.err = "no slot for a W tile"; break; }
-                overwrite(q, o.out, false);
-                d.slotC = q;
-                if (need_store(o.out)) pending.push_back({q, o.out, -1, -1.0});
+                S[q].id = o.inplace_to; S[q].clean = false;
+                if (need_store(o.inplace_to)) pending.push_back({q, o.inplace_to, -1, -1.0});
                 break;
             }
             case DOP_CH_POTRF: {
@@ -556,6 +629,7 @@ inline std::string dag_verify(const DagProgram& P) {
         switch (d.type) {
         case DOP_MMA_NT: case DOP_P1_MMA: case DOP_P2_MMA: rec(d.slotA, 0, i, false); rec(d.slotB, 0, i, false); break;
         case DOP_PUT: rec(d.slotC, 0, i, true); break;
+        case DOP_GET: rec(d.slotC, 0, i, false); break;
         case DOP_TRSM: rec(d.slotC, 0, i, true); rec(d.slotB, 0, i, false); break;
         case DOP_P1_FIN: rec(d.slotA, 0, i, false); rec(d.slotC, 0, i, true); break;
         default: break;
@@ -606,6 +680,7 @@ inline std::string dag_verify(const DagProgram& P) {
         return "";
     };
     std::string e;
+    int acc_owner = -1;                               // tile whose partial result the bulk accumulators hold
     const int NT = P.NT;
     std::vector<char> haveL(NT * NT, 0), haveW(NT * NT, 0);
     while (ib < nb || ic < nc) {
@@ -632,12 +707,23 @@ inline std::string dag_verify(const DagProgram& P) {
             const int I = d.I, J = d.J, k = d.k;
             switch (d.type) {
             case DOP_MMA_NT:
+                if (acc_owner != tid_of(TK_U, I, J)) { snprintf(buf, sizeof buf, "bulk op %d updates accumulators that belong to another tile", ib); return buf; }
                 if (!(e = expect(d.slotA, tid_of(TK_L, I, k), "A", 0, ib)).empty()) return e;
                 if (!(e = expect(d.slotB, tid_of(TK_L, J, k), "B", 0, ib)).empty()) return e;
                 break;
             case DOP_PUT:
-                if (!(e = clobber(d.slotC, "put", 0, ib)).empty()) return e;
-                content[d.slotC] = tid_of(TK_U, I, J);
+                if (acc_owner != tid_of(k == TK_T ? TK_T : TK_U, I, J)) { snprintf(buf, sizeof buf, "bulk op %d puts accumulators that belong to another tile", ib); return buf; }
+                if (d.flags & DOPF_INPLACE) { if (!(e = expect(d.slotC, tid_of(TK_P, I, J), "put over", 0, ib)).empty()) return e; }
+                else if (!(e = clobber(d.slotC, "put", 0, ib)).empty()) return e;
+                content[d.slotC] = tid_of(k, I, J);
+                acc_owner = -1;
+                break;
+            case DOP_GET:
+                if (!(e = expect(d.slotC, tid_of(TK_P, I, J), "get", 0, ib)).empty()) return e;
+                acc_owner = tid_of(TK_U, I, J);
+                break;
+            case DOP_BUILD:
+                acc_owner = tid_of(TK_U, I, J);
                 break;
             case DOP_TRSM:
                 if (!(e = expect(d.slotC, tid_of(TK_U, I, J), "C", 0, ib)).empty()) return e;
@@ -645,16 +731,20 @@ inline std::string dag_verify(const DagProgram& P) {
                 content[d.slotC] = tid_of(TK_L, I, J); haveL[I * NT + J] = 1;
                 break;
             case DOP_P1_MMA:
+                if (d.flags & DOPF_FIRST) acc_owner = tid_of(TK_T, I, J);
+                if (acc_owner != tid_of(TK_T, I, J)) { snprintf(buf, sizeof buf, "bulk op %d accumulates into accumulators that belong to another tile", ib); return buf; }
                 if (!(e = expect(d.slotA, tid_of(TK_L, I, k), "A", 0, ib)).empty()) return e;
                 if (!(e = expect(d.slotB, tid_of(TK_W, k, J), "B", 0, ib)).empty()) return e;
                 break;
             case DOP_P1_FIN:
                 if (!(e = expect(d.slotA, tid_of(TK_W, I, I), "A", 0, ib)).empty()) return e;
-                if (!(e = clobber(d.slotC, "fin", 0, ib)).empty()) return e;
+                if (!(e = expect(d.slotC, tid_of(TK_T, I, J), "C", 0, ib)).empty()) return e;
                 if (d.slotC == d.slotA) return "P1_FIN output slot equals its operand";
                 content[d.slotC] = tid_of(TK_W, I, J); haveW[I * NT + J] = 1;
                 break;
             case DOP_P2_MMA:
+                if (d.flags & DOPF_FIRST) acc_owner = tid_of(TK_W + 8, I, J);
+                if (acc_owner != tid_of(TK_W + 8, I, J)) { snprintf(buf, sizeof buf, "bulk op %d accumulates into accumulators that belong to another tile", ib); return buf; }
                 if (!(e = expect(d.slotA, tid_of(TK_W, k, I), "A", 0, ib)).empty()) return e;
                 if (!(e = expect(d.slotB, tid_of(TK_W, k, J), "B", 0, ib)).empty()) return e;
                 break;

@@ -279,11 +279,13 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             const DagOp* op = a.chain + j;
             const int K = __ldg(&op->I), sA = __ldg(&op->slotA), sC = __ldg(&op->slotC), wo = __ldg(&op->wait_other);
             PHBC(56);
+            TRC(j, 0);
             if (wo > 0) {
                 if (lane == 0) spin_until(&sync[0], NWARPS * wo);
                 __syncwarp();
             }
             PHEC(56);
+            TRC(j, 1);
             double* A = slots + (size_t)sA * TILE_ELEMS;
             double* W = slots + (size_t)sC * TILE_ELEMS;
             PHBC(57);
@@ -297,6 +299,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             fence_proxy_async();          // W (and, in FACTOR mode, L) may be written through by a bulk store
             chain_bar();
             if (cw == 0 && lane == 0) sync_arrive(&sync[1]);      // event 2j + 1: L(K,K) and W(K,K) are final
+            TRC(j, 2);
             PHBC(59);
             // z_K = W_KK (r_K - sum_{J<K} L_KJ z_J)
             if (cw == 0) {
@@ -324,6 +327,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             }
             chain_bar();
             if (cw == 0 && lane == 0) sync_arrive(&sync[1]);      // event 2j + 2: z_K (and alpha_K) published
+            TRC(j, 3);
             PHEC(59);
         }
         PHEC(55);
@@ -360,6 +364,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     int4 n0 = __ldg(nxp), n1 = __ldg(nxp + 1), n2 = __ldg(nxp + 2);
     for (int i = 0; i < a.nbulk; ++i) {
         PHB(41);
+        TRB(i, 0);
         const DagOp* op = a.bulk + i;
         const int type = n0.x, I = n0.y, J = n0.z, k = n0.w;
         const int sA = n1.x, sB = n1.y, sC = n1.z;
@@ -397,6 +402,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             }
         PHE(42);
         PHB(42 + type);
+        TRB(i, 1);
         const double* A = slots + (size_t)(sA < 0 ? 0 : sA) * TILE_ELEMS;
         const double* Bt = slots + (size_t)(sB < 0 ? 0 : sB) * TILE_ELEMS;
         double* C = slots + (size_t)(sC < 0 ? 0 : sC) * TILE_ELEMS;
@@ -437,6 +443,9 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             acc_store(acc, C, wt);
             fence_proxy_async();
             break;
+        case DOP_GET:
+            acc_load(acc, C, wt);
+            break;
         case DOP_TRSM: {
             // L(I,J) = U(I,J) W(J,J)^T in place (W lower triangular: k <= n), then accw_I += L(I,J) z_J
             double r2[4][2][2];
@@ -469,9 +478,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             tile_mma<false, false, false>(acc, A, Bt, wt, (k == J) ? wt.n0 : 0, TS);
             break;
         case DOP_P1_FIN: {
-            // W(I,J) = -W(I,I) acc  (W(I,I) lower triangular: k <= m), then alpha_J += W(I,J)^T z_I
-            acc_store(acc, C, wt);
-            named_bar_sync(1, DAG_BULK_THREADS);
+            // W(I,J) = -W(I,I) T(I,J) in place  (W(I,I) lower triangular: k <= m), then alpha_J += W(I,J)^T z_I
             double r2[4][2][2];
             acc_zero(r2);
             tile_mma<false, false, true>(r2, A, C, wt, 0, wt.m0 + 32);
@@ -517,6 +524,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
         default: break;
         }
         PHE(42 + type);
+        TRB(i, 2);
         __syncwarp();
         if (lane == 0) sync_arrive(&sync[0]);
     }

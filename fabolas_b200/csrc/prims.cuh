@@ -28,6 +28,9 @@ namespace fab {
 __device__ long long g_phase[64];
 #define PHB(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
 #define PHE(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
+__device__ long long g_trace[2][128][4];
+#define TRB(i, k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && (i) < 128) g_trace[0][i][k] = clock64(); } while (0)
+#define TRC(i, k) do { if (threadIdx.x == 256 && blockIdx.x == 0 && (i) < 128) g_trace[1][i][k] = clock64(); } while (0)
 #define PHBC(id) do { if (threadIdx.x == 256 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
 #define PHEC(id) do { if (threadIdx.x == 256 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
 #else
@@ -35,6 +38,8 @@ __device__ long long g_phase[64];
 #define PHE(id) do {} while (0)
 #define PHBC(id) do {} while (0)
 #define PHEC(id) do {} while (0)
+#define TRB(i, k) do {} while (0)
+#define TRC(i, k) do {} while (0)
 #endif
 
 constexpr double kTiny = 1.25e-12;        // george's default white noise (oracle/george_oracle.py TINY)

@@ -42,3 +42,21 @@ print(f"config {cfg}: cycles per launch (CTA 0), us at {mhz:.0f} MHz")
 for k in sorted(NAMES):
     c = buf[k] / REP
     print(f"{k:3d} {NAMES[k]:40s} {c:12.0f} cyc {c / mhz:9.2f} us")
+
+if "--trace" in sys.argv:
+    tr = (ctypes.c_longlong * (2 * 128 * 4))()
+    lib.fab_debug_trace_read(tr)
+    prog = (ctypes.c_int * (4 * 128))()
+    NT = (w["X"].shape[0] + 63) // 64
+    n = lib.fab_debug_program_read(NT, 6, 3 if GRAD else 0, prog, 128)
+    names = ["NOP", "BUILD", "MMA_NT", "PUT", "TRSM", "P1_MMA", "P1_FIN", "P2_MMA", "CH", "GET"]
+    t0 = tr[0]
+    us = lambda c: (c - t0) / mhz
+    print("bulk ops (CTA 0, last launch): index, op, arrive, start, end [us]; wait = start - arrive")
+    for i in range(n):
+        a, b, c = tr[4 * i], tr[4 * i + 1], tr[4 * i + 2]
+        print(f"B{i:3d} {names[prog[4*i]]:7s}({prog[4*i+1]},{prog[4*i+2]}) k={prog[4*i+3]}  {us(a):8.2f} {us(b):8.2f} {us(c):8.2f}  wait {us(b)-us(a):6.2f}  run {us(c)-us(b):6.2f}")
+    print("chain ops: top, after wait, tiles published, vectors published [us]")
+    for j in range(NT):
+        o = 4 * 128 + 4 * j
+        print(f"C{j}  {us(tr[o]):8.2f} {us(tr[o+1]):8.2f} {us(tr[o+2]):8.2f} {us(tr[o+3]):8.2f}")
