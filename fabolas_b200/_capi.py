@@ -21,6 +21,8 @@ DEFAULT_LIB = os.path.join(_HERE, "_lib", "libfabolas_b200.so")
 
 FAB_FAMILY_M52 = 0
 FAB_FAMILY_M52_BASIS = 1
+FAB_PRIOR_FABOLAS = 0      # fabolas.log_likelihood's prior (fabolas.py:27-50)
+FAB_PRIOR_ES = 1           # entropy_search's log_prob prior (entropy_search.py:49-69)
 
 _c_int = ctypes.c_int
 _c_dbl = ctypes.c_double
@@ -44,6 +46,10 @@ SIGNATURES = {
     "fab_es_information_gain_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
+    "fab_mcmc_run": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, ctypes.c_ulonglong,
+                              ctypes.c_longlong, _c_dbl, _vp, _vp, _vp]),
+    "fab_mcmc_log_prior": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp]),
+    "fab_ctx_debug_set_mcmc_ctas": (_c_int, [_vp, _c_int]),
     "fab_ctx_debug_set_max_slots": (_c_int, [_vp, _c_int]),
     "fab_ctx_debug_force_slices": (_c_int, [_vp, _c_int]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
@@ -313,6 +319,39 @@ class Engine:
         self._check(self.lib.fab_kernel_matrix(self._ctx, family, nu_code, _ptr(theta), B, _ptr(Xa), Na, _ptr(Xb), Nb, D,
                                                amp_mult, _ptr(K), _ptr(dK)), "fab_kernel_matrix")
         return (K, dK) if grad else K
+
+    # ------------------------------------------------------------------------------------------
+    def mcmc_run(self, prior: int, coords, nsteps: int, log_prob=None, seed: int = 0, iter0: int = 0, a: float = 2.0,
+                 store_chain: bool = True, naccepted=None):
+        """emcee's run_mcmc on the device (one persistent kernel): returns (coords, log_prob, chain, chain_lp,
+        naccepted); coords (K, P) and log_prob are advanced IN PLACE when they are tensors on the device."""
+        coords = self.tensor(coords)
+        if coords.dim() != 2:
+            raise FabolasError("coords must be (nwalkers, ndim)")
+        K, P = coords.shape
+        init = log_prob is None
+        lp = self.empty(K) if init else self.tensor(log_prob)
+        chain = self.empty(nsteps, K, P) if store_chain else None
+        chain_lp = self.empty(nsteps, K) if store_chain else None
+        nacc = torch.zeros(K, dtype=torch.int64, device=self.device) if naccepted is None else naccepted
+        self._check(self.lib.fab_mcmc_run(self._ctx, int(prior), _ptr(coords), _ptr(lp), K, P, int(nsteps), int(init),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(iter0), float(a), _ptr(chain),
+                                          _ptr(chain_lp), _ptr(nacc)), "fab_mcmc_run")
+        return coords, lp, chain, chain_lp, nacc
+
+    def log_prior(self, prior: int, params, want_theta: bool = False):
+        """Log-prior of the reference's sampler log-probabilities for rows of walker positions (K, P)."""
+        p = self.tensor(params)
+        K, P = p.shape
+        out = self.empty(K)
+        theta = torch.zeros(K, P - 1, dtype=torch.float64, device=self.device) if want_theta else None
+        yerr2 = torch.zeros(K, dtype=torch.float64, device=self.device) if want_theta else None
+        self._check(self.lib.fab_mcmc_log_prior(self._ctx, int(prior), _ptr(p), K, P, _ptr(out), _ptr(theta),
+                                                _ptr(yerr2)), "fab_mcmc_log_prior")
+        return (out, theta, yerr2) if want_theta else out
+
+    def debug_set_mcmc_ctas(self, n: int):
+        self._check(self.lib.fab_ctx_debug_set_mcmc_ctas(self._ctx, int(n)), "fab_ctx_debug_set_mcmc_ctas")
 
     def debug_factor(self, b: int) -> torch.Tensor:
         L = self.empty(self.N, self.N)

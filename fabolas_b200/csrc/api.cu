@@ -5,6 +5,7 @@
 #include "epmgp.cuh"
 #include "ig.cuh"
 #include "kmat.cuh"
+#include "mcmc.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -48,6 +49,12 @@ struct fab_ctx {
     int smem_optin = 232448;
     int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
     int force_slices = 0;        // test knob: never keep all coordinates resident in the gradient kernel
+    // device-resident ensemble sampler (mcmc.cuh): per-CTA scratch records
+    double* mcTheta = nullptr; double* mcYerr2 = nullptr; double* mcLl = nullptr; double* mcQ = nullptr;
+    int* mcInfo = nullptr; unsigned long long* mcKeys = nullptr; int* mcOrder = nullptr; unsigned* mcBar = nullptr;
+    size_t cap_mc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int num_sms = 148;
+    int mcmc_max_ctas = 0;       // test knob: cap the sampler's grid (0 = one CTA per proposal, up to the SM count)
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -120,6 +127,8 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
     cudaFuncSetAttribute(epmgp_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(es_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(gp_predict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(mcmc_stretch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - MCMC_STATIC_SMEM);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->num_sms = v;
 #endif
     *out = c;
     return FAB_OK;
@@ -138,6 +147,8 @@ int fab_ctx_destroy(fab_ctx* c) {
 #endif
     for (auto& kv : c->dag) { cudaFree(kv.second.bulk); cudaFree(kv.second.chain); }
     cudaFree(c->wkSpill);
+    cudaFree(c->mcTheta); cudaFree(c->mcYerr2); cudaFree(c->mcLl); cudaFree(c->mcQ); cudaFree(c->mcInfo);
+    cudaFree(c->mcKeys); cudaFree(c->mcOrder); cudaFree(c->mcBar);
     cudaFree(c->wk.Lw); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw);
     delete c;
     return FAB_OK;
@@ -219,15 +230,16 @@ int fab_gp_set_data(fab_ctx* c, int family, const double* X, int N, int D, const
     return FAB_OK;
 }
 
-// One launch of the fused kernel.  mode: DAG_LL (ll only), DAG_FACTOR (+ L tiles in the workspace),
-// DAG_FIT (+ W = L^-1 tiles and alpha in the workspace), DAG_GRAD (+ gradient).
-static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info, double* grad,
-                      int mode) {
+// Everything one launch of the fused evaluation needs for B walker records: the static tile program for
+// (NT, slots, mode) -- built and uploaded once --, the per-walker workspaces and the shared-memory size.
+// mode: DAG_LL (ll only), DAG_FACTOR (+ L tiles in the workspace), DAG_FIT (+ W = L^-1 tiles and alpha in the
+// workspace), DAG_GRAD (+ gradient).  `smem_limit`: dynamic shared memory the launching kernel may use.
+static int dag_setup(fab_ctx* c, int B, int mode, size_t smem_limit, DagArgs* out, size_t* smem_out) {
     const GpData& gd = c->gd;
     const int ntiles = gd.NT * (gd.NT + 1) / 2;
     int nslot = c->max_slots;
-    int resident = (!c->force_slices && dag_smem_bytes(nslot, gd.d, gd.Np) <= (size_t)c->smem_optin) ? 1 : 0;
-    while (nslot > 0 && dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0) > (size_t)c->smem_optin) --nslot;
+    int resident = (!c->force_slices && dag_smem_bytes(nslot, gd.d, gd.Np) <= smem_limit) ? 1 : 0;
+    while (nslot > 0 && dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0) > smem_limit) --nslot;
     if (nslot < 4) return fail(c, FAB_EUNSUPPORTED, "not enough shared memory for the fused kernel");
     const long long key = ((long long)gd.NT << 16) | (nslot << 4) | mode;
     auto it = c->dag.find(key);
@@ -253,18 +265,31 @@ static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int 
     if ((rc = ensure(c, &c->wk.alpha, &c->capA, (size_t)B * gd.Np)) != FAB_OK) return rc;
     if (mode == DAG_FACTOR && (rc = ensure(c, &c->wkSpill, &c->capSpill, (size_t)B * gd.NT * TILE_ELEMS)) != FAB_OK) return rc;
     DagArgs a;
-    a.gd = gd; a.wk = c->wk; a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info; a.grad = grad;
+    a.gd = gd; a.wk = c->wk; a.theta = nullptr; a.yerr2 = nullptr; a.ll = nullptr; a.info = nullptr; a.grad = nullptr;
     a.bulk = dv.bulk; a.chain = dv.chain; a.nbulk = dv.nbulk; a.nchain = dv.nchain;
     a.nslot = nslot; a.mode = mode; a.resident = resident; a.ntiles = ntiles; a.wk_spill = c->wkSpill;
-    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
-    FAB_LAUNCH(gp_dag_kernel, B, DAG_THREADS, dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0), c->stream, a);
-    FAB_CUDA(c, cudaGetLastError());
-    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
+    *out = a;
+    *smem_out = dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0);
     c->resident = false;
     c->es_ready = false;
     c->wsB = B;
     c->factored = mode == DAG_FACTOR;
     c->inverted = mode == DAG_FIT;
+    return FAB_OK;
+}
+
+// One launch of the fused kernel (one CTA per walker).
+static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info, double* grad,
+                      int mode) {
+    DagArgs a;
+    size_t smem = 0;
+    const int rc = dag_setup(c, B, mode, (size_t)c->smem_optin, &a, &smem);
+    if (rc != FAB_OK) return rc;
+    a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info; a.grad = grad;
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
+    FAB_LAUNCH(gp_dag_kernel, B, DAG_THREADS, smem, c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
     return FAB_OK;
 }
 
@@ -455,6 +480,76 @@ int fab_ei_batch(fab_ctx* c, const double* mu, const double* var, int B, int M, 
     a.mu = mu; a.var = var; a.M = M; a.y_max = y_max; a.xi = xi; a.ei = ei; a.best_val = best_val; a.best_idx = best_idx;
     FAB_LAUNCH(ei_argmax_kernel, B, NTHREADS, 0, c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
+    return FAB_OK;
+}
+
+// The whole ensemble chain on the device: one persistent cooperative launch (mcmc.cuh).
+int fab_mcmc_run(fab_ctx* c, int prior, double* coords, double* log_prob, int K, int P, int nsteps, int init_lp,
+                 unsigned long long seed, long long iter0, double a_scale, double* chain, double* chain_lp,
+                 long long* naccepted) {
+    if (!c) return FAB_EINVAL;
+    if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
+    if (!coords || !log_prob || nsteps < 0 || !(a_scale > 1.0)) return fail(c, FAB_EINVAL, "bad argument");
+    if (K < 2 || (K & 1)) return fail(c, FAB_EINVAL, "an even number of walkers >= 2 is required for the red/blue stretch move");
+    const GpData& gd = c->gd;
+    if (prior != MCMC_PRIOR_FABOLAS && prior != MCMC_PRIOR_ES) return fail(c, FAB_EINVAL, "unknown prior");
+    if ((prior == MCMC_PRIOR_FABOLAS) != (gd.family == FAB_FAMILY_M52_BASIS))
+        return fail(c, FAB_EINVAL, "prior 0 (fabolas.py) goes with the basis-kernel family, prior 1 (entropy_search.py) with the Matern family");
+    if (P != gd.Pk + 1) return fail(c, FAB_EINVAL, "walker dimension must be len(kernel) + 1 (the noise)");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    int grid = K / 2;
+#ifdef FAB_CUSIM
+    grid = 1;                                   // the emulator runs CTAs one after the other: no grid barrier
+#else
+    if (grid > c->num_sms) grid = c->num_sms;   // one CTA per SM (shared memory), all co-resident
+#endif
+    if (c->mcmc_max_ctas > 0 && grid > c->mcmc_max_ctas) grid = c->mcmc_max_ctas;
+    McmcArgs m;
+    size_t smem = 0;
+    int rc = dag_setup(c, grid, DAG_LL, (size_t)c->smem_optin - MCMC_STATIC_SMEM, &m.dag, &smem);
+    if (rc != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcTheta, &c->cap_mc[0], (size_t)grid * gd.Pk)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcYerr2, &c->cap_mc[1], (size_t)grid)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcLl, &c->cap_mc[2], (size_t)grid)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcQ, &c->cap_mc[3], (size_t)grid * P)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcInfo, &c->cap_mc[4], (size_t)grid)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcKeys, &c->cap_mc[5], (size_t)grid * K)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcOrder, &c->cap_mc[6], (size_t)grid * K)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->mcBar, &c->cap_mc[7], (size_t)1)) != FAB_OK) return rc;
+    FAB_CUDA(c, cudaMemsetAsync(c->mcBar, 0, sizeof(unsigned), c->stream));
+    m.dag.theta = c->mcTheta; m.dag.yerr2 = c->mcYerr2; m.dag.ll = c->mcLl; m.dag.info = c->mcInfo;
+    m.coords = coords; m.lp = log_prob; m.q = c->mcQ; m.keys = c->mcKeys; m.order = c->mcOrder;
+    m.K = K; m.P = P; m.prior = prior; m.nsteps = nsteps; m.init_lp = init_lp != 0;
+    m.seed = seed; m.iter0 = iter0; m.a = a_scale;
+    m.chain = chain; m.chain_lp = chain_lp; m.nacc = naccepted; m.gbar = c->mcBar;
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
+#ifdef FAB_CUSIM
+    FAB_LAUNCH(mcmc_stretch_kernel, grid, DAG_THREADS, smem, c->stream, m);
+#else
+    void* params[] = {&m};
+    FAB_CUDA(c, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mcmc_stretch_kernel), dim3(grid), dim3(DAG_THREADS),
+                                            params, smem, c->stream));
+#endif
+    FAB_CUDA(c, cudaGetLastError());
+    if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
+    return FAB_OK;
+}
+
+int fab_mcmc_log_prior(fab_ctx* c, int prior, const double* p, int K, int P, double* out, double* theta, double* yerr2) {
+    if (!c) return FAB_EINVAL;
+    if (!p || !out || K < 1) return fail(c, FAB_EINVAL, "bad argument");
+    if (prior != MCMC_PRIOR_FABOLAS && prior != MCMC_PRIOR_ES) return fail(c, FAB_EINVAL, "unknown prior");
+    const int Pk = P - 1, d = prior == MCMC_PRIOR_FABOLAS ? Pk - 3 : Pk - 1;
+    if (d < 1 || d > MAX_D) return fail(c, FAB_EINVAL, "need 1 <= d <= 8 Matern axes");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    FAB_LAUNCH(mcmc_prior_kernel, (K + 127) / 128, 128, 0, c->stream, p, K, P, prior, d, Pk, out, theta, yerr2);
+    FAB_CUDA(c, cudaGetLastError());
+    return FAB_OK;
+}
+
+int fab_ctx_debug_set_mcmc_ctas(fab_ctx* c, int n) {
+    if (!c || n < 0) return FAB_EINVAL;
+    c->mcmc_max_ctas = n;
     return FAB_OK;
 }
 

@@ -208,12 +208,14 @@ __device__ __forceinline__ void contract_acc(const double (&acc)[4][2][2], doubl
     }
 }
 
-// 12 warps: 65536 / 384 = 170 -> 168 registers per thread.
-#define FAB_DAG_KERNEL_ATTR __global__ void __launch_bounds__(DAG_THREADS, 1)
-FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
-    FAB_DYN_SMEM(smem_raw);
+// One evaluation by the whole CTA (DAG_THREADS threads): walker record `b` of a.theta / a.yerr2 / a.ll /
+// a.info / a.grad and of the per-walker workspaces.  A CTA may run any number of evaluations one after the
+// other (the device-resident ensemble sampler, mcmc.cuh): `first` marks the CTA's first one (exp table and
+// mbarriers are set up once), `phases` carries the mbarrier parities of the bulk warps across evaluations, and
+// the caller separates two evaluations by a __syncthreads().
+__device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned char* smem_raw, unsigned& phases,
+                                         const bool first) {
     const GpData& gd = a.gd;
-    const int b = blockIdx.x;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int Np = gd.Np, N = gd.N, d = gd.d, Pk = gd.Pk;
     const int SL = slice_doubles(d);
@@ -249,7 +251,7 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     double* Lx = a.wk_spill ? a.wk_spill + (size_t)b * gd.NT * TILE_ELEMS : nullptr;
     auto ws_tile = [&](int tile) { return tile < a.ntiles ? Lw + (size_t)tile * TILE_ELEMS : Lx + (size_t)(tile - a.ntiles) * TILE_ELEMS; };
 
-    exp_table_fill(etab);
+    if (first) exp_table_fill(etab);
     for (int i = tid; i < Np; i += DAG_THREADS) accw[i] = 0.0;
     if (a.resident) {
         for (int e = tid; e < N * gd.D; e += DAG_THREADS) {
@@ -264,10 +266,11 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
         }
     }
     if (tid == 0) {
-        for (int s = 0; s < MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
+        if (first)
+            for (int s = 0; s < MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
         sync[0] = 0; sync[1] = 0; sync[2] = 0; sync[3] = 0;
     }
-    __syncthreads();                      // the only block-wide barrier: the two streams part here
+    __syncthreads();                      // the only block-wide barrier of an evaluation: the two streams part here
 
     if (w >= NWARPS) {
         // ======================================= CHAIN stream =======================================
@@ -345,13 +348,12 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
             sync[2] = first_fail;
             sync_arrive(&sync[1]);        // "everything of the chain, including the failure flag, is published"
         }
-        return;
+        return;                           // (inlined: leaves dag_eval, not the kernel)
     }
 
     // ========================================= BULK stream =========================================
     const WarpTile wt = warp_tile();
     const int g = lane >> 2, t = lane & 3;
-    unsigned phases = 0u;                 // mbarrier phase parity per slot (uniform)
     double acc[4][2][2];
     acc_zero(acc);
     double* gsum_w = red + w * (MAX_PK + 1);   // this warp's gradient partial sums (contract_acc)
@@ -558,6 +560,14 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     if (tid == 0) bulk_s2g_wait_all();
     PHE(51);
     PHE(40);
+}
+
+// 12 warps: 65536 / 384 = 170 -> 168 registers per thread.
+#define FAB_DAG_KERNEL_ATTR __global__ void __launch_bounds__(DAG_THREADS, 1)
+FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
+    FAB_DYN_SMEM(smem_raw);
+    unsigned phases = 0u;                 // mbarrier phase parity per slot (uniform over the bulk warps)
+    dag_eval(a, blockIdx.x, smem_raw, phases, true);
 }
 
 }  // namespace fab

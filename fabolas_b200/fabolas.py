@@ -10,11 +10,11 @@ from scipy.optimize import minimize
 
 from . import epmgp, runtime
 from .acquisitions import information_gain_cost, information_gain_cost_batch, prepare_entropy_search
-from ._capi import FAB_FAMILY_M52_BASIS
+from ._capi import FAB_FAMILY_M52_BASIS, FAB_PRIOR_FABOLAS
 from .george import GP, ConstantKernel, LinearKernel, Matern52Kernel
 from .horseshoe import Horseshoe
 from .models import ModelBatch
-from .sampler import EnsembleSampler
+from .sampler import DeviceEnsembleSampler, EnsembleSampler
 
 
 def lognorm_logpdf(x, s=1.0):
@@ -62,8 +62,10 @@ def log_likelihood_batch(params, engine):
     return out
 
 
-def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None):
-    """fabolas.py:69-117: K walkers, 100 burn-in + 500 steps, last positions (K, P)."""
+def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None, on_device=True):
+    """fabolas.py:69-117: K walkers, 100 burn-in + 500 steps, last positions (K, P).  on_device (default): the
+    whole chain is one persistent kernel (DeviceEnsembleSampler); otherwise the emcee-shaped host loop calls the
+    batched GPU likelihood once per half-step."""
     X = np.asarray(X, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
     engine = engine or runtime.new_engine()
@@ -71,6 +73,11 @@ def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None):
     # ConstantKernel over all ndim axes, hence amp_mult = ndim
     engine.set_data(FAB_FAMILY_M52_BASIS, X, y, float(np.mean(y)), float(X.shape[1]))
     ndim = X.shape[1] + 3                      # len(kernel) + 1
+    if on_device:
+        sampler = DeviceEnsembleSampler(K, ndim, engine, FAB_PRIOR_FABOLAS)
+        state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, store=False)
+        sampler.reset()
+        return sampler.run_mcmc(state, iterations, store=False).coords
     sampler = EnsembleSampler(K, ndim, log_likelihood_batch, args=[engine], vectorize=True)
     state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, rstate0=np.random.get_state())
     sampler.reset()

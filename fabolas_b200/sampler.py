@@ -93,3 +93,68 @@ class EnsembleSampler:
     @property
     def acceptance_fraction(self):
         return self.naccepted / max(self.iteration, 1)
+
+
+class DeviceEnsembleSampler:
+    """The same emcee surface with the WHOLE chain on the GPU: `fab_mcmc_run` runs every half-step's proposals,
+    log-probabilities (the reference's own: prior 0 = fabolas.py:16-66, prior 1 = entropy_search.py:40-77, on
+    the engine's data) and acceptance tests inside one persistent kernel.
+    `log_prob_fn` is therefore not a callable but the prior id; the random stream is Philox keyed by `seed`
+    (numpy's global state, which the reference seeds through rstate0, only picks the seed)."""
+
+    def __init__(self, nwalkers, ndim, engine, prior, a=2.0, seed=None):
+        if nwalkers < 2 or nwalkers % 2:
+            raise ValueError("an even number of walkers >= 2 is required for the red/blue stretch move")
+        self.nwalkers, self.ndim, self.engine, self.prior, self.a = nwalkers, ndim, engine, int(prior), float(a)
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._steps_taken = 0           # position in the Philox stream; reset() keeps it (a new chain, fresh numbers)
+        self.reset()
+
+    def reset(self):
+        self._chain, self._log_prob = None, None
+        self._nacc = None
+        self.iteration = 0
+
+    def run_mcmc(self, initial_state, nsteps, rstate0=None, store=True, **kwargs):
+        if isinstance(initial_state, State):
+            coords, lp = initial_state.coords, initial_state.log_prob
+        else:
+            coords, lp = initial_state, None
+        import torch
+        coords = self.engine.tensor(coords.clone() if isinstance(coords, torch.Tensor)
+                                    else np.array(coords, dtype=np.float64, copy=True))
+        if tuple(coords.shape) != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions")
+        coords, lp, chain, chain_lp, nacc = self.engine.mcmc_run(
+            self.prior, coords, nsteps, log_prob=lp, seed=self.seed, iter0=self._steps_taken, a=self.a,
+            store_chain=store, naccepted=self._nacc)
+        self._steps_taken += nsteps
+        self.iteration += nsteps
+        self._nacc = nacc
+        if store:
+            self._chain = chain if self._chain is None else torch.cat([self._chain, chain])
+            self._log_prob = chain_lp if self._log_prob is None else torch.cat([self._log_prob, chain_lp])
+        lp_host = lp.cpu().numpy()
+        if np.any(np.isnan(lp_host)):
+            raise ValueError("Probability function returned NaN")
+        st = State(coords.cpu().numpy(), lp_host)
+        st.device_coords, st.device_log_prob = coords, lp
+        return st
+
+    def get_chain(self):
+        return np.empty((0, self.nwalkers, self.ndim)) if self._chain is None else self._chain.cpu().numpy()
+
+    def get_log_prob(self):
+        return np.empty((0, self.nwalkers)) if self._log_prob is None else self._log_prob.cpu().numpy()
+
+    @property
+    def chain(self):
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    @property
+    def naccepted(self):
+        return np.zeros(self.nwalkers) if self._nacc is None else self._nacc.cpu().numpy().astype(np.float64)
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / max(self.iteration, 1)

@@ -132,6 +132,33 @@ int fab_es_information_gain_batch(fab_ctx* ctx, const double* Xc, int M, double*
 int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta, int B, const double* Xa,
                       int Na, const double* Xb, int Nb, int D, double amp_mult, double* K, double* dK);
 
+/* emcee's EnsembleSampler(K, P, log_prob).run_mcmc(p0, nsteps) with the stretch move (a = 2, red/blue halves)
+ * as the reference drives it (fabolas.py:103-117, entropy_search.py:80-85), with the reference's own
+ * log-probability -- prior 0: fabolas.log_likelihood (fabolas.py:16-66, goes with FAB_FAMILY_M52_BASIS),
+ * prior 1: entropy_search's log_prob (entropy_search.py:40-77, FAB_FAMILY_M52) -- evaluated on the data of
+ * fab_gp_set_data.  The whole chain runs as ONE persistent kernel: every half-step's K/2 proposals are drawn,
+ * evaluated and accepted on the device; nothing returns to the host between steps.
+ *   coords    K x P   walker positions, in/out (P = len(kernel) + 1: [cov, lamb..., noise])
+ *   log_prob  K       in/out; computed from coords first when init_lp != 0 (emcee: state.log_prob is None)
+ *   seed, iter0       Philox4x32-10 stream: a pure function of (seed, iter0 + step, walker); continue a chain
+ *                     with iter0 = steps already taken
+ *   chain     nsteps x K x P or NULL (emcee's get_chain()); chain_lp  nsteps x K or NULL (get_log_prob())
+ *   naccepted K int64 or NULL: accepted moves, accumulated
+ * K even, 2 <= K; any K runs (CTAs loop over proposals beyond the number of SMs).  MCMC is stochastic: parity with
+ * emcee is distributional, and exact against a host replay of the same Philox stream (tests/test_mcmc.py).       */
+int fab_mcmc_run(fab_ctx* ctx, int prior, double* coords, double* log_prob, int K, int P, int nsteps, int init_lp,
+                 unsigned long long seed, long long iter0, double a, double* chain, double* chain_lp,
+                 long long* naccepted);
+
+/* The log-prior part of those two log-probabilities for K rows p (K x P), and the george parameter vector
+ * (K x (P-1), may be NULL) and yerr^2 (K, may be NULL) their likelihood is evaluated at; -inf outside the
+ * support (theta row then zero).  horseshoe.py:10-33 with scipy.special.exp1's algorithm, lognorm(s=1).       */
+int fab_mcmc_log_prior(fab_ctx* ctx, int prior, const double* p, int K, int P, double* out, double* theta,
+                       double* yerr2);
+
+/* Debug / test knob: cap the sampler's grid (0 = default: one CTA per proposal up to the SM count).           */
+int fab_ctx_debug_set_mcmc_ctas(fab_ctx* ctx, int n);
+
 /* Debug / test knob: cap the number of shared-memory tile slots (4..6) so that small problems
  * exercise the L2/HBM tile-streaming path of the fused GP kernel.                                  */
 int fab_ctx_debug_set_max_slots(fab_ctx* ctx, int n);
