@@ -293,6 +293,23 @@ def run_ours(args):
               "nan_flags": int(flag.sum()), "epmgp_info_max": int(ep_info.max())}
     eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])       # back to the ll+grad problem state
 
+    # ---- the caller of the path: fabolas.sample_hypers' chain (fabolas.py:103-117: 100 burn-in + 500
+    # steps, 128 walkers) as ONE persistent kernel -- prior, stretch proposals, likelihood and acceptance on the device
+    from fabolas_b200._capi import FAB_PRIOR_FABOLAS
+    p0 = eng.tensor(np.random.default_rng(20260009 + rank).uniform(0, 1, (Bg, P)))
+    c_, lp_, _, _, _ = eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 20, seed=1, store_chain=False)     # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    c_, lp_, _, _, nacc_ = eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 600, seed=2, store_chain=False)
+    e1.record(); torch.cuda.synchronize()
+    ms_mcmc = e0.elapsed_time(e1)
+    mcmc_out = {"value": (Bg + 600 * Bg) / (ms_mcmc * 1e-3), "unit": "log-prob evals/s inside one persistent sampler kernel",
+                "walkers": Bg, "steps": 600, "ms_per_chain": ms_mcmc, "us_per_half_step": ms_mcmc / 1200 * 1e3,
+                "acceptance_fraction": float(nacc_.double().mean().item() / 600),
+                "finite_log_prob": int(torch.isfinite(lp_).sum().item())}
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+
     # parity spot check of the timed path against the oracle (2 walkers; cheap)
     ll, g = step_resident()
     torch.cuda.synchronize()
@@ -352,6 +369,7 @@ def run_ours(args):
                                      "flops_per_eval": f_ll, "achieved": ll_tf, "frac": ll_tf / peak},
                          "whole_step_frac": Bg * f_llg / (ms_step * 1e-3) / 1e12 / peak},
             "es_acquisition": es_out,
+            "mcmc_device_sampler": mcmc_out,
             "cpu_baseline": None if cpu_val is None else {
                 "value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{n_evals} ll+grad evals of the same workload, one single-threaded numpy/scipy oracle "

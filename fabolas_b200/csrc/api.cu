@@ -54,6 +54,7 @@ struct fab_ctx {
     int* mcInfo = nullptr; unsigned long long* mcKeys = nullptr; int* mcOrder = nullptr; unsigned* mcBar = nullptr;
     size_t cap_mc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int num_sms = 148;
+    double* eiVal = nullptr; long long* eiIdx = nullptr; size_t cap_ei[2] = {0, 0};   // per-chunk argmax partials
     int mcmc_max_ctas = 0;       // test knob: cap the sampler's grid (0 = one CTA per proposal, up to the SM count)
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
@@ -147,6 +148,7 @@ int fab_ctx_destroy(fab_ctx* c) {
 #endif
     for (auto& kv : c->dag) { cudaFree(kv.second.bulk); cudaFree(kv.second.chain); }
     cudaFree(c->wkSpill);
+    cudaFree(c->eiVal); cudaFree(c->eiIdx);
     cudaFree(c->mcTheta); cudaFree(c->mcYerr2); cudaFree(c->mcLl); cudaFree(c->mcQ); cudaFree(c->mcInfo);
     cudaFree(c->mcKeys); cudaFree(c->mcOrder); cudaFree(c->mcBar);
     cudaFree(c->wk.Lw); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw);
@@ -337,14 +339,21 @@ static int launch_predict(fab_ctx* c, const double* T, long long T_bstride, int 
     a.mu = mu; a.var = var; a.cov = cov; a.dotvec = dotvec; a.dot = dot; a.vcol = vcol; a.vcol_index = vcol_index;
     const bool want_cov = cov != nullptr;
     if (want_cov && M > 64) return fail(c, FAB_EUNSUPPORTED, "full predictive covariance is limited to M <= 64 points");
-    const size_t s64 = predict_smem_bytes(64, gd.NT, gd.Np, gd.d, want_cov);
-    const size_t s32 = predict_smem_bytes(32, gd.NT, gd.Np, gd.d, false);
-    if (s64 <= (size_t)c->smem_optin) {
-        FAB_LAUNCH(gp_predict_kernel<64>, dim3((M + 63) / 64, c->wsB), NTHREADS, s64, c->stream, a);
-    } else if (!want_cov && s32 <= (size_t)c->smem_optin) {
-        FAB_LAUNCH(gp_predict_kernel<32>, dim3((M + 31) / 32, c->wsB), NTHREADS, s32, c->stream, a);
+    // widest candidate block that fits, with two W tile buffers when they fit as well
+    int CB = 0, nbuf = 0;
+    for (int cb : {64, 32}) {
+        if (cb == 32 && want_cov) break;
+        for (int nb : {2, 1})
+            if (!CB && predict_smem_bytes(cb, gd.NT, gd.Np, gd.d, want_cov, nb) <= (size_t)c->smem_optin) { CB = cb; nbuf = nb; }
+        if (CB) break;
+    }
+    if (!CB) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA prediction kernel");
+    a.nbuf = nbuf;
+    const size_t smem = predict_smem_bytes(CB, gd.NT, gd.Np, gd.d, want_cov, nbuf);
+    if (CB == 64) {
+        FAB_LAUNCH(gp_predict_kernel<64>, dim3((M + 63) / 64, c->wsB), NTHREADS, smem, c->stream, a);
     } else {
-        return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA prediction kernel");
+        FAB_LAUNCH(gp_predict_kernel<32>, dim3((M + 31) / 32, c->wsB), NTHREADS, smem, c->stream, a);
     }
     FAB_CUDA(c, cudaGetLastError());
     return FAB_OK;
@@ -478,8 +487,24 @@ int fab_ei_batch(fab_ctx* c, const double* mu, const double* var, int B, int M, 
     FAB_CUDA(c, cudaSetDevice(c->device));
     EiArgs a;
     a.mu = mu; a.var = var; a.M = M; a.y_max = y_max; a.xi = xi; a.ei = ei; a.best_val = best_val; a.best_idx = best_idx;
-    FAB_LAUNCH(ei_argmax_kernel, B, NTHREADS, 0, c->stream, a);
+    // enough CTAs to stream the moments at HBM speed whatever B is (one model x 1M candidates: config 4)
+    int G = (int)(((long long)M + 4 * NTHREADS - 1) / (4 * NTHREADS));
+    const int gmax = (4 * c->num_sms + B - 1) / B;
+    if (G > gmax) G = gmax;
+    if (G < 1) G = 1;
+    const long long chunk = ((long long)M + G - 1) / G;
+    G = (int)(((long long)M + chunk - 1) / chunk);
+    if (G > 1) {
+        int rc;
+        if ((rc = ensure(c, &c->eiVal, &c->cap_ei[0], (size_t)B * G)) != FAB_OK) return rc;
+        if ((rc = ensure(c, &c->eiIdx, &c->cap_ei[1], (size_t)B * G)) != FAB_OK) return rc;
+    }
+    FAB_LAUNCH(ei_argmax_kernel, dim3(G, B), NTHREADS, 0, c->stream, a, chunk, c->eiVal, c->eiIdx);
     FAB_CUDA(c, cudaGetLastError());
+    if (G > 1 && (best_val || best_idx)) {
+        FAB_LAUNCH(ei_argmax_final_kernel, B, 32, 0, c->stream, a, G, c->eiVal, c->eiIdx);
+        FAB_CUDA(c, cudaGetLastError());
+    }
     return FAB_OK;
 }
 

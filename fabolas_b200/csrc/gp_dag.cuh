@@ -82,33 +82,37 @@ __device__ __forceinline__ void build_acc(double (&acc)[4][2][2], const double* 
         const int ip = q >> 1, j = q & 1;
         const int lj0 = wt.n0 + 8 * j + 2 * t;
         const int bcol = (wt.n0 >> 3) + j;
-        double2 zc[DD];
-#pragma unroll
-        for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
-        const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
         double tmp[2][2];
+        tmp[0][0] = tmp[0][1] = tmp[1][0] = tmp[1][1] = 0.0;
+        // diagonal tile: both 8x8 blocks of this pass lie above the block diagonal -> zero, nothing to evaluate
+        if (!(I == J && bcol > (wt.m0 >> 3) + 2 * ip + 1)) {
+            double2 zc[DD];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int li = wt.m0 + 8 * (2 * ip + r) + g;
-            const int gi = TS * I + li;
-            const bool upper = I == J && bcol > (li >> 3);
-            double zr[DD];
+            for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
+            const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
 #pragma unroll
-            for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
-            const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
+            for (int r = 0; r < 2; ++r) {
+                const int li = wt.m0 + 8 * (2 * ip + r) + g;
+                const int gi = TS * I + li;
+                const bool upper = I == J && bcol > (li >> 3);
+                double zr[DD];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int gj = TS * J + lj0 + e;
-                double r2 = 0.0;
+                for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
+                const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
 #pragma unroll
-                for (int k = 0; k < DD; ++k) {
-                    const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
-                    r2 = fma(dz, dz, r2);
+                for (int e = 0; e < 2; ++e) {
+                    const int gj = TS * J + lj0 + e;
+                    double r2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DD; ++k) {
+                        const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                        r2 = fma(dz, dz, r2);
+                    }
+                    double v = h.amp * matern52_fast_value(r2, etab) * fma(ur, e ? uc.y : uc.x, cb);
+                    v = (gi == gj) ? v + h.diag_add : v;
+                    v = (gi >= N || gj >= N) ? ((gi == gj) ? 1.0 : 0.0) : v;
+                    tmp[r][e] = upper ? 0.0 : v;
                 }
-                double v = h.amp * matern52_fast_value(r2, etab) * fma(ur, e ? uc.y : uc.x, cb);
-                v = (gi == gj) ? v + h.diag_add : v;
-                v = (gi >= N || gj >= N) ? ((gi == gj) ? 1.0 : 0.0) : v;
-                tmp[r][e] = upper ? 0.0 : v;
             }
         }
         switch (q) {                        // static accumulator indices
@@ -143,6 +147,7 @@ __device__ __forceinline__ void contract_acc(const double (&acc)[4][2][2], doubl
         const int ip = q >> 1, j = q & 1;
         const int lj0 = wt.n0 + 8 * j + 2 * t;
         const int bcol = (wt.n0 >> 3) + j;
+        if (I == J && bcol > (wt.m0 >> 3) + 2 * ip + 1) continue;     // weight 0 on both blocks of this pass
         double kinv[2][2];
         switch (q) {                        // static accumulator indices
         case 0: kinv[0][0] = acc[0][0][0]; kinv[0][1] = acc[0][0][1]; kinv[1][0] = acc[1][0][0]; kinv[1][1] = acc[1][0][1]; break;
@@ -439,7 +444,8 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             break;
         }
         case DOP_MMA_NT:
-            tile_mma<false, true, true>(acc, A, Bt, wt, 0, TS);
+            if (I != J) tile_mma<false, true, true>(acc, A, Bt, wt, 0, TS);
+            else tile_mma_lower<false, true, true>(acc, A, Bt, wt, 0);
             break;
         case DOP_PUT:
             acc_store(acc, C, wt);
@@ -509,7 +515,8 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         case DOP_P2_MMA:
             if (flags & DOPF_FIRST) acc_zero(acc);
             // W(I,I) is lower triangular: (W_II)[k'][m] = 0 for k' < m
-            tile_mma<true, false, false>(acc, A, Bt, wt, (k == I) ? wt.m0 : 0, TS);
+            if (I != J) tile_mma<true, false, false>(acc, A, Bt, wt, (k == I) ? wt.m0 : 0, TS);
+            else tile_mma_lower<true, false, false>(acc, A, Bt, wt, (k == I) ? wt.m0 : 0);
             if (flags & DOPF_LAST) {
                 PHB(50);
                 const double* ar_p = a.resident ? alv + TS * I : al_r;

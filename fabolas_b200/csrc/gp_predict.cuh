@@ -28,12 +28,65 @@ struct PredictArgs {
     double* dot;             // B x M or null:  dot[b][c] = sum_obs V[obs][c] * dotvec[b][obs]
     double* vcol;            // B x Np or null: column `vcol_index` of V = W K*^T (first block only)
     int vcol_index;
+    int nbuf;                // W tile buffers in shared memory: 2 (load of tile t+1 overlaps the product of tile t) or 1
 };
 
-__host__ __device__ inline size_t predict_smem_bytes(int CB, int NT, int Np, int d, bool cov) {
-    size_t doubles = (size_t)NT * TS * CB + TILE_ELEMS + (cov ? TS * CB : 0) + (size_t)(d + 3) * Np + (size_t)(d + 1) * CB +
-                     3 * 8 * CB + 16;
+// Shared memory: the panel (NT x 64 x CB), then a region used twice -- first by the scaled observation
+// coordinates, the basis column and alpha while the panel is generated, then by the W tile buffers of the
+// product loop --, the optional covariance scratch, the candidate coordinates, the exp table, partial sums.
+__host__ __device__ inline size_t predict_union_doubles(int Np, int d, int nbuf) {
+    const size_t coords = (size_t)(d + 2) * Np, wb = (size_t)nbuf * TILE_ELEMS;
+    return coords > wb ? coords : wb;
+}
+__host__ __device__ inline size_t predict_smem_bytes(int CB, int NT, int Np, int d, bool cov, int nbuf) {
+    size_t doubles = (size_t)NT * TS * CB + predict_union_doubles(Np, d, nbuf) + (cov ? TS * CB : 0) +
+                     (size_t)(d + 1) * CB + EXP_TAB_N + 3 * 8 * CB + 16;
     return doubles * 8 + 64;
+}
+
+// One 8-row strip of the cross-covariance panel per warp and pass: lane = candidate column, four rows in
+// flight (independent Matern chains), candidate coordinates in registers, observation coordinates broadcast.
+template <int DD, int CB>
+__device__ __forceinline__ void predict_panel(double* Ks, const double* zs, const double* us, const double* al,
+                                              const double* tz, const double* tu, const Hyper& h, int family, int N,
+                                              int Np, int NT, int ncand, const double* __restrict__ etab,
+                                              double (&pmu)[CB / 32]) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool basis = family == 1;
+#pragma unroll
+    for (int q = 0; q < CB / 32; ++q) {
+        const int c = lane + 32 * q;
+        double tc[DD];
+#pragma unroll
+        for (int k = 0; k < DD; ++k) tc[k] = tz[k * CB + c];
+        const double tuc = basis ? tu[c] * h.inv_g2 : 0.0;
+        const double cbv = basis ? h.cb : 1.0;
+        const bool cok = c < ncand;
+        double pm = 0.0;
+        for (int J = 0; J < NT; ++J) {
+            double* P = Ks + (size_t)J * TS * CB;
+#pragma unroll
+            for (int r4 = 0; r4 < 2; ++r4) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int gi = TS * J + 8 * w + 4 * r4 + u;
+                    double r2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DD; ++k) {
+                        const double dz = zs[k * Np + gi] - tc[k];
+                        r2 = fma(dz, dz, r2);
+                    }
+                    const double kv = h.amp * matern52_fast_value(r2, etab) * fma(us[gi], tuc, cbv);
+                    v[u] = (gi < N && cok) ? kv : 0.0;
+                    pm = fma(v[u], al[gi], pm);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) P[tixw<CB>(8 * w + 4 * r4 + u, c)] = v[u];
+            }
+        }
+        pmu[q] = pm;
+    }
 }
 
 template <int CB>
@@ -49,21 +102,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(PredictArgs a) 
     const bool want_cov = a.cov != nullptr;
 
     double* Ks = reinterpret_cast<double*>(smem_raw);            // NT panels of 64 x CB
-    double* Wbuf = Ks + (size_t)NT * TS * CB;
-    double* Vscr = Wbuf + TILE_ELEMS;
-    double* zs = Vscr + (want_cov ? TS * CB : 0);
+    double* uni = Ks + (size_t)NT * TS * CB;                      // coordinates, then W tile buffers
+    double* zs = uni;
     double* us = zs + (size_t)d * Np;
     double* al = us + Np;
-    double* dv = al + Np;
-    double* tz = dv + Np;                                          // d x CB
+    double* Wbuf = uni;
+    double* Vscr = uni + predict_union_doubles(Np, d, a.nbuf);
+    double* tz = Vscr + (want_cov ? TS * CB : 0);                  // d x CB
     double* tu = tz + (size_t)d * CB;                              // CB
-    double* part = tu + CB;                                        // 3 x 8 x CB
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(part + 3 * 8 * CB);
+    double* etab = tu + CB;
+    double* part = etab + EXP_TAB_N;                               // 3 x 8 x CB
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(part + 3 * 8 * CB);   // [2]
 
     const Hyper h = decode_hyper(gd, a.theta + (size_t)b * gd.Pk, a.yerr2[b]);
     const double* Lw = a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS;
     const int c_base = blk * CB;
 
+    exp_table_fill(etab);
     for (int e = tid; e < N * D; e += NTHREADS) {
         const int i = e / D, k = e - i * D;
         const double x = __ldg(&gd.X[e]);
@@ -77,7 +132,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(PredictArgs a) 
         }
         if (gd.family != 1 && i < N) us[i] = 0.0;
         al[i] = a.wk.alpha[(size_t)b * Np + i];
-        dv[i] = a.dotvec ? a.dotvec[(size_t)b * Np + i] : 0.0;
     }
     for (int e = tid; e < CB * D; e += NTHREADS) {
         const int c = e / D, k = e - c * D;
@@ -87,65 +141,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(PredictArgs a) 
         if (k == d) tu[c] = x;
     }
     if (gd.family != 1) for (int c = tid; c < CB; c += NTHREADS) tu[c] = 0.0;
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     __syncthreads();
 
     // ---- cross-covariance panel K*^T (obs x cand) + mean partials ----
     double pmu[CB / 32];
-#pragma unroll
-    for (int q = 0; q < CB / 32; ++q) pmu[q] = 0.0;
-    for (int J = 0; J < NT; ++J) {
-        double* P = Ks + (size_t)J * TS * CB;
-#pragma unroll 1
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = 8 * w + rr, gi = TS * J + r;
-#pragma unroll
-            for (int q = 0; q < CB / 32; ++q) {
-                const int c = lane + 32 * q;
-                double v = 0.0;
-                if (gi < N && c_base + c < a.M) {
-                    double r2 = 0.0;
-                    for (int k = 0; k < d; ++k) {
-                        const double dz = zs[k * Np + gi] - tz[k * CB + c];
-                        r2 = fma(dz, dz, r2);
-                    }
-                    double m, gf;
-                    matern52(r2, m, gf);
-                    v = h.amp * m;
-                    if (gd.family == 1) v *= fma(us[gi] * tu[c], h.inv_g2, h.cb);
-                    pmu[q] = fma(v, al[gi], pmu[q]);
-                }
-                P[tixw<CB>(r, c)] = v;
-            }
-        }
+#define FAB_PANEL_CASE(DD) case DD: predict_panel<DD, CB>(Ks, zs, us, al, tz, tu, h, gd.family, N, Np, NT, a.M - c_base, etab, pmu); break;
+    switch (d) {
+        FAB_PANEL_CASE(1) FAB_PANEL_CASE(2) FAB_PANEL_CASE(3) FAB_PANEL_CASE(4)
+        FAB_PANEL_CASE(5) FAB_PANEL_CASE(6) FAB_PANEL_CASE(7) FAB_PANEL_CASE(8)
     }
+#undef FAB_PANEL_CASE
 #pragma unroll
     for (int q = 0; q < CB / 32; ++q) part[w * CB + lane + 32 * q] = pmu[q];
+    fence_proxy_async();                   // the coordinate region is about to be overwritten by bulk copies
     __syncthreads();
 
-    // ---- V = W K*^T, reduced on the fly ----
+    // ---- V = W K*^T, reduced on the fly; W tiles stream through `nbuf` buffers ----
     const WarpTile wt = (CB == 64) ? warp_tile() : warp_tile_32();
     double css[NJ][2], cdot[NJ][2];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) css[j][0] = css[j][1] = cdot[j][0] = cdot[j][1] = 0.0;
     double cacc[4][2][2];
     acc_zero(cacc);
-    unsigned phase = 0;
+    const int nb = a.nbuf;
+    const int ntile = NT * (NT + 1) / 2;       // tiles are consumed in workspace order: (0,0) (1,0) (1,1) (2,0) ...
+    int tcount = 0;
+    if (tid == 0) bulk_g2s(Wbuf, Lw, TILE_BYTES, &bar[0]);
     for (int I = 0; I < NT; ++I) {
         double acc[MI][NJ][2];
         acc_zero(acc);
-        for (int J = 0; J <= I; ++J) {
-            if (tid == 0) bulk_g2s(Wbuf, Lw + (size_t)tri_index(I, J) * TILE_ELEMS, TILE_BYTES, bar);
-            mbar_wait(bar, phase & 1u);
-            ++phase;
+        for (int J = 0; J <= I; ++J, ++tcount) {
+            const int cur = (nb == 2) ? (tcount & 1) : 0;
+            if (nb == 2 && tid == 0 && tcount + 1 < ntile)     // the other buffer was released by the barrier below
+                bulk_g2s(Wbuf + (size_t)(cur ^ 1) * TILE_ELEMS, Lw + (size_t)(tcount + 1) * TILE_ELEMS, TILE_BYTES, &bar[cur ^ 1]);
+            mbar_wait(&bar[cur], (nb == 2) ? ((tcount >> 1) & 1u) : (tcount & 1u));
             // W_II is lower triangular: columns k > m contribute nothing
-            tile_mma<false, false, false, MI, NJ, TS, CB>(acc, Wbuf, Ks + (size_t)J * TS * CB, wt, 0,
+            tile_mma<false, false, false, MI, NJ, TS, CB>(acc, Wbuf + (size_t)cur * TILE_ELEMS, Ks + (size_t)J * TS * CB, wt, 0,
                                                           (J == I) ? wt.m0 + 8 * MI : TS);
-            __syncthreads();               // everyone done with Wbuf before the next bulk copy lands
+            __syncthreads();               // everyone done with this buffer before the next bulk copy lands in it
+            if (nb == 1 && tid == 0 && tcount + 1 < ntile)
+                bulk_g2s(Wbuf, Lw + (size_t)(tcount + 1) * TILE_ELEMS, TILE_BYTES, &bar[0]);
         }
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
-            const double dvr = dv[TS * I + wt.m0 + 8 * i + g];
+            const double dvr = a.dotvec ? __ldg(&a.dotvec[(size_t)b * Np + TS * I + wt.m0 + 8 * i + g]) : 0.0;
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
 #pragma unroll
@@ -254,14 +294,20 @@ __device__ __forceinline__ double ei_value(double mu, double var, double y_max, 
     return sd * (u * cdf + pdf);
 }
 
-__global__ void __launch_bounds__(NTHREADS) ei_argmax_kernel(EiArgs a) {
+// Grid (G, B): CTA (x, b) scans candidates [x * chunk, (x + 1) * chunk) of model b.  G == 1 writes the result,
+// otherwise the (value, index) pair of the chunk goes to part_val / part_idx [b * G + x] and ei_argmax_final_kernel
+// finishes (np.argmax: the first occurrence of the maximum wins at every level).
+__global__ void __launch_bounds__(NTHREADS) ei_argmax_kernel(EiArgs a, long long chunk, double* part_val,
+                                                             long long* part_idx) {
     __shared__ double sval[NWARPS];
     __shared__ long long sidx[NWARPS];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const double ym = a.y_max[b];
     double best = -INFINITY;
     long long bi = -1;
-    for (long long c = tid; c < a.M; c += NTHREADS) {
+    const long long c0 = (long long)blockIdx.x * chunk;
+    const long long c1 = (c0 + chunk < (long long)a.M) ? c0 + chunk : (long long)a.M;
+    for (long long c = c0 + tid; c < c1; c += NTHREADS) {
         const double v = ei_value(a.mu[(size_t)b * a.M + c], a.var[(size_t)b * a.M + c], ym, a.xi);
         if (a.ei) a.ei[(size_t)b * a.M + c] = v;
         if (v > best) { best = v; bi = c; }             // first maximum wins within a thread (ascending c)
@@ -277,8 +323,34 @@ __global__ void __launch_bounds__(NTHREADS) ei_argmax_kernel(EiArgs a) {
     if (tid == 0) {
         for (int q = 1; q < NWARPS; ++q)
             if (sval[q] > best || (sval[q] == best && sidx[q] >= 0 && (bi < 0 || sidx[q] < bi))) { best = sval[q]; bi = sidx[q]; }
+        if (gridDim.x == 1) {
+            if (a.best_val) a.best_val[b] = best;
+            if (a.best_idx) a.best_idx[b] = bi;          // np.argmax: first occurrence of the maximum
+        } else {
+            part_val[(size_t)b * gridDim.x + blockIdx.x] = best;
+            part_idx[(size_t)b * gridDim.x + blockIdx.x] = bi;
+        }
+    }
+}
+
+__global__ void ei_argmax_final_kernel(EiArgs a, int G, const double* part_val, const long long* part_idx) {
+    const int b = blockIdx.x, lane = threadIdx.x;       // one warp per model
+    double best = -INFINITY;
+    long long bi = -1;
+    for (int x = lane; x < G; x += 32) {                // chunks ascend with x: the first maximum wins
+        const double v = part_val[(size_t)b * G + x];
+        const long long i = part_idx[(size_t)b * G + x];
+        if (v > best || (v == best && i >= 0 && (bi < 0 || i < bi))) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ov; bi = oi; }
+    }
+    if (lane == 0) {
         if (a.best_val) a.best_val[b] = best;
-        if (a.best_idx) a.best_idx[b] = bi;              // np.argmax: first occurrence of the maximum
+        if (a.best_idx) a.best_idx[b] = bi;
     }
 }
 

@@ -37,12 +37,16 @@ __device__ __forceinline__ int tixw(int r, int c) { return r * LD + (c ^ ((r & 3
 struct WarpTile {
     int m0, n0;   // origin of this warp's block inside the output tile
 };
-// 8 warps as 2 x 4 blocks of 32 x 16 over a 64 x 64 output
+// 8 warps as 2 x 4 blocks of 32 x 16 over a 64 x 64 output.  Warps w and w + 4 share an SM sub-partition (and
+// its DMMA pipe); the lower row of blocks is laid out in reverse column order so that the two column blocks of
+// a sub-partition are 16 s and 16 (3 - s): products whose k-range depends on the column block (triangular
+// right-hand operand: k < n0 + 16 or k >= n0) then cost every sub-partition the same 5/8 of a full product
+// instead of costing one of them all of it (profiles/r01y_*).
 __device__ __forceinline__ WarpTile warp_tile() {
     const int w = threadIdx.x >> 5;
     WarpTile wt;
     wt.m0 = (w >> 2) * 32;
-    wt.n0 = (w & 3) * 16;
+    wt.n0 = ((w >> 2) ? 3 - (w & 3) : (w & 3)) * 16;
     return wt;
 }
 // 8 warps as 4 x 2 blocks of 16 x 16 over a 64 x 32 output
@@ -114,6 +118,44 @@ __device__ __forceinline__ void tile_mma(double (&acc)[MI][NJ][2], const double*
 #pragma unroll
             for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+}
+
+// The same product when only the blocks on and below the block diagonal of the 64 x 64 result are needed (a
+// diagonal tile of the covariance update or of K^-1): a warp whose 32 x 16 block lies above the diagonal does
+// nothing, one whose upper 16 rows do computes the lower 16 only (8-row granularity of the decision: rows
+// [r, r + 16) are needed iff their last row block reaches the warp's first column block).
+template <bool TA, bool TB, bool NEG, int I0>
+__device__ __forceinline__ void tile_mma_from_row(double (&acc)[4][2][2], const double* __restrict__ A,
+                                                  const double* __restrict__ B, WarpTile wt, int k_lo, int k_hi) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int sg = (g & 3) << 2, st = t << 2;
+    int a_off[4], b_off[2];
+#pragma unroll
+    for (int i = I0; i < 4; ++i) a_off[i] = TA ? (t * TS + ((wt.m0 + 8 * i + g) ^ st)) : ((wt.m0 + 8 * i + g) * TS + t);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b_off[j] = TB ? ((wt.n0 + 8 * j + g) * TS + t) : (t * TS + ((wt.n0 + 8 * j + g) ^ st));
+#pragma unroll 4
+    for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
+        const int krow = k0 ^ sg;
+        double a[4], b[2];
+#pragma unroll
+        for (int i = I0; i < 4; ++i) {
+            const double v = A[a_off[i] + (TA ? k0 * TS : krow)];
+            a[i] = NEG ? -v : v;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) b[j] = B[b_off[j] + (TB ? krow : k0 * TS)];
+#pragma unroll
+        for (int i = I0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+template <bool TA, bool TB, bool NEG>
+__device__ __forceinline__ void tile_mma_lower(double (&acc)[4][2][2], const double* __restrict__ A,
+                                               const double* __restrict__ B, WarpTile wt, int k_lo) {
+    if (wt.n0 <= wt.m0 + 8) tile_mma_from_row<TA, TB, NEG, 0>(acc, A, B, wt, k_lo, TS);
+    else if (wt.n0 <= wt.m0 + 24) tile_mma_from_row<TA, TB, NEG, 2>(acc, A, B, wt, k_lo, TS);
 }
 
 // ---------------------------------------------------------------------------------------------

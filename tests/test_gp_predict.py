@@ -73,6 +73,21 @@ def test_ei_argmax_emulated(sim_engine):
         assert int(bi[b]) == int(np.argmax(full)) and float(bv[b]) == full.max()
 
 
+def test_ei_argmax_chunked_emulated(sim_engine):
+    """More candidates than one CTA scans: per-chunk partials + final reduction; the FIRST maximum wins across chunks."""
+    rng = np.random.default_rng(1)
+    M = 5000
+    mu, var = rng.standard_normal((2, M)), rng.uniform(0.1, 1, (2, M))
+    for c in (4100, 1300, 2999):                              # the same (largest) EI in three different chunks
+        mu[0, c], var[0, c] = 9.0, 1.0
+    mu[1, M - 1], var[1, M - 1] = 9.0, 1.0                    # maximum in the last, ragged chunk
+    ei, bv, bi = sim_engine.expected_improvement(mu, var, np.array([0.0, 0.0]))
+    assert int(bi[0]) == 1300 and int(bi[1]) == M - 1
+    assert np.array_equal(bi.numpy(), np.argmax(ei.numpy(), axis=1)) and np.array_equal(bv.numpy(), ei.numpy().max(axis=1))
+    _, bv2, bi2 = sim_engine.expected_improvement(mu, var, np.array([0.0, 0.0]), want_ei=False)
+    assert np.array_equal(bi2.numpy(), bi.numpy()) and np.array_equal(bv2.numpy(), bv.numpy())
+
+
 def test_predict_requires_fit_emulated(sim_engine):
     from fabolas_b200 import FabolasError
     sim_engine.set_data(0, np.zeros((4, 1)) + np.arange(4)[:, None], np.arange(4.0), 0.0, 1)
