@@ -190,7 +190,37 @@ def run_ours(args):
     g_host = torch.empty(Bg, P, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # 256 MB > 126 MB L2
 
+    # N > 1: the exchange of the step (every rank ends up with every walker's ll + gradient) is fused into the kernel:
+    # each CTA stores its walker's row into every rank's gather buffer over NVLink peer memory and a one-thread
+    # kernel waits for all rows (fab_gp_loglik_exchange / fab_peer_wait).  --exchange nccl keeps the kernel +
+    # NCCL all-gather pair; it is also the fallback when the peers cannot be mapped (CUDA IPC unavailable).
+    exchange = "none"
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "peer":
+            try:
+                eng.peer_setup(Bg)
+            except Exception as e:                       # noqa: BLE001 -- reported in the JSON line
+                exchange = f"nccl (peer mapping failed: {str(e)[:80]})"
+            ok_all = torch.tensor([1.0 if exchange == "peer" else 0.0], device="cuda")
+            dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+            if ok_all.item() == 0.0 and exchange == "peer":
+                exchange = "nccl (a peer could not map)"
+        if exchange == "peer":                           # one-time check against the collective it replaces
+            ll, g, info = eng.loglik(theta_d, yerr2_d, grad=True)
+            mine = torch.cat([g, ll[:, None], info.double()[:, None]], 1).contiguous()
+            ref = torch.empty(world * Bg, P + 2, dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(ref, mine)
+            eng.loglik_exchange(theta_d, yerr2_d, grad=True)
+            rows = eng.peer_wait()
+            torch.cuda.synchronize()
+            assert torch.equal(rows, ref) and not eng.peer_error(), "fused exchange differs from the NCCL all-gather"
+
     def step_resident():
+        if exchange == "peer":
+            ll, g, info = eng.loglik_exchange(theta_d, yerr2_d, grad=True, out=(ll_loc, g_loc, info_loc))
+            eng.peer_wait()
+            return ll, g
         ll, g, info = eng.loglik(theta_d, yerr2_d, grad=True, out=(ll_loc, g_loc, info_loc))
         if world > 1:
             dist.all_gather_into_tensor(packed_all, packed)
@@ -351,11 +381,14 @@ def run_ours(args):
             "config": {"workload": "BASELINE configs[1]: CNN-CIFAR10 space (5 hyper-parameters) + s, N=256, D=6, P=9, "
                                    "128 walkers per GPU, Matern52 x (linear+const) basis kernel",
                        "walkers_per_gpu": Bg, "N": N, "D": D, "l2_flush_between_steps": True,
-                       "parallelism": f"walkers sharded x{world}, one NCCL all-gather of the packed (grad | ll) block per step"},
+                       "parallelism": f"walkers sharded x{world}; exchange of the per-walker (grad | ll | info) rows per step: "
+                                      + {"none": "none (one GPU)", "peer": "fused into the kernel (NVLink peer stores into every "
+                                         "rank's gather buffer + arrival counter; one-thread wait kernel)"}.get(
+                                             exchange, "NCCL all-gather after the kernel [" + exchange + "]")},
             "e2e": {"value": world * Bg / (ms_e2e / K * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(theta_h.numel() * 8 + yerr2_h.numel() * 8),
                     "d2h_bytes_per_step": int(ll_host.numel() * 8 + g_host.numel() * 8)},
-            "gpu_launches": K,
+            "gpu_launches": K * (2 if exchange == "peer" else 1),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "pipe": "FP64 tensor cores (DMMA mma.sync m8n8k4.f64; tcgen05 has no FP64 kind)",
                          "kernel": "gp_dag_kernel", "achieved": kern_tf, "peak": peak,
@@ -387,6 +420,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-walker results reach every rank (fused peer stores, or NCCL all-gather)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg (profiling runs)")
     ap.add_argument("--cpu-per-core", type=int, default=640,
                     help="ll+grad evaluations per host core of the bounded CPU-oracle sample (~10-30 s of CPU work)")

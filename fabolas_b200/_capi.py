@@ -46,6 +46,12 @@ SIGNATURES = {
     "fab_es_information_gain_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
+    "fab_peer_alloc": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp]),
+    "fab_peer_connect": (_c_int, [_vp, _vp]),
+    "fab_gp_loglik_exchange": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
+    "fab_peer_wait": (_c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)]),
+    "fab_peer_error": (_c_int, [_vp]),
+    "fab_peer_free": (_c_int, [_vp]),
     "fab_mcmc_run": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, ctypes.c_ulonglong,
                               ctypes.c_longlong, _c_dbl, _vp, _vp, _vp]),
     "fab_mcmc_log_prior": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp]),
@@ -319,6 +325,70 @@ class Engine:
         self._check(self.lib.fab_kernel_matrix(self._ctx, family, nu_code, _ptr(theta), B, _ptr(Xa), Na, _ptr(Xb), Nb, D,
                                                amp_mult, _ptr(K), _ptr(dK)), "fab_kernel_matrix")
         return (K, dK) if grad else K
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU likelihood step with the exchange fused into the kernel (peer memory over NVLink / NVSwitch)
+    def peer_setup(self, rows_per_rank: int, group=None):
+        """Allocate this rank's gather buffers, exchange the CUDA IPC handles over torch.distributed and map the
+        peers.  Without an initialised process group: a world of one (the local rank is its own peer)."""
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        rank, world = (dist.get_rank(group), dist.get_world_size(group)) if multi else (0, 1)
+        h = (ctypes.c_ubyte * 64)()
+        self._check(self.lib.fab_peer_alloc(self._ctx, rank, world, int(rows_per_rank), ctypes.cast(h, _vp)),
+                    "fab_peer_alloc")
+        if multi:
+            mine = torch.tensor(list(h), dtype=torch.uint8, device=self.device)
+            allh = torch.empty(world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            buf = (ctypes.c_ubyte * (64 * world))(*allh.cpu().tolist())
+            self._check(self.lib.fab_peer_connect(self._ctx, ctypes.cast(buf, _vp)), "fab_peer_connect")
+            dist.barrier(group=group)
+        else:
+            self._check(self.lib.fab_peer_connect(self._ctx, None), "fab_peer_connect")
+        self._peer_views = {}
+        self.peer_world, self.peer_rank, self.peer_rows = world, rank, int(rows_per_rank)
+
+    def loglik_exchange(self, theta, yerr2, grad: bool = False, out=None):
+        """loglik() on this rank's walkers whose result rows also land in every rank's gather buffer."""
+        theta, yerr2 = self._theta(theta, yerr2)
+        B = theta.shape[0]
+        if out is not None:
+            ll, g, info = out if grad else (out[0], None, out[-1])
+        else:
+            ll = self.empty(B)
+            info = self.empty(B, dtype=torch.int32)
+            g = self.empty(B, self.Pk + 1) if grad else None
+        self._check(self.lib.fab_gp_loglik_exchange(self._ctx, _ptr(theta), _ptr(yerr2), B, _ptr(ll), _ptr(g), _ptr(info)),
+                    "fab_gp_loglik_exchange")
+        return (ll, g, info) if grad else (ll, info)
+
+    def peer_wait(self) -> torch.Tensor:
+        """Enqueue the wait for every rank's rows of the last exchanged step; returns the (world * B, Pk + 3) view of
+        this rank's gather buffer: [grad (Pk+1) | ll | info] per walker, rank-major."""
+        ptr, rows, rd = _vp(), _c_int(), _c_int()
+        self._check(self.lib.fab_peer_wait(self._ctx, ctypes.byref(ptr), ctypes.byref(rows), ctypes.byref(rd)), "fab_peer_wait")
+        key = ptr.value
+        if key not in self._peer_views:
+            shape = (rows.value, rd.value)
+            if self.device.type == "cuda":
+                class _Raw:
+                    __cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (key, False), "version": 3,
+                                                "strides": None}
+                self._peer_views[key] = torch.as_tensor(_Raw(), device=self.device)
+            else:
+                import numpy as np
+                arr = np.ctypeslib.as_array(ctypes.cast(key, ctypes.POINTER(_c_dbl)), shape=shape)
+                self._peer_views[key] = torch.from_numpy(arr)
+        return self._peer_views[key]
+
+    def peer_error(self) -> bool:
+        return bool(self.lib.fab_peer_error(self._ctx))
+
+    def peer_free(self):
+        self._peer_views = {}
+        self.peer_world = self.peer_rows = 0
+        self._check(self.lib.fab_peer_free(self._ctx), "fab_peer_free")
 
     # ------------------------------------------------------------------------------------------
     def mcmc_run(self, prior: int, coords, nsteps: int, log_prob=None, seed: int = 0, iter0: int = 0, a: float = 2.0,

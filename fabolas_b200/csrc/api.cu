@@ -49,6 +49,15 @@ struct fab_ctx {
     int smem_optin = 232448;
     int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
     int force_slices = 0;        // test knob: never keep all coordinates resident in the gradient kernel
+    // peer exchange of the likelihood step (gp_dag.cuh PeerTable): one IPC-exported allocation per rank holding two
+    // gather buffers (step parity) + arrival counter + error flag; the peers' mappings
+    struct Peer {
+        int world = 0, rank = 0, rows_per_rank = 0, row_doubles = 0;
+        void* base[FAB_MAX_PEERS] = {nullptr};      // base[rank] is the local allocation, the others are IPC mappings
+        size_t buf_bytes = 0;
+        bool connected = false;
+        unsigned long long steps = 0;
+    } peer;
     // device-resident ensemble sampler (mcmc.cuh): per-CTA scratch records
     double* mcTheta = nullptr; double* mcYerr2 = nullptr; double* mcLl = nullptr; double* mcQ = nullptr;
     int* mcInfo = nullptr; unsigned long long* mcKeys = nullptr; int* mcOrder = nullptr; unsigned* mcBar = nullptr;
@@ -105,6 +114,16 @@ __global__ void untile_kernel(const double* __restrict__ Lw, double* __restrict_
     }
 }
 
+void peer_release(fab_ctx* c) {
+#ifndef FAB_CUSIM
+    for (int r = 0; r < c->peer.world; ++r)
+        if (r != c->peer.rank && c->peer.base[r]) cudaIpcCloseMemHandle(c->peer.base[r]);
+#endif
+    if (c->peer.world > 0 && c->peer.base[c->peer.rank]) cudaFree(c->peer.base[c->peer.rank]);
+    c->peer = fab_ctx::Peer();
+}
+inline size_t peer_ctrl_offset(const fab_ctx::Peer& p) { return 2 * p.buf_bytes; }     // counter, then error flag
+
 }  // namespace
 
 extern "C" {
@@ -148,6 +167,7 @@ int fab_ctx_destroy(fab_ctx* c) {
 #endif
     for (auto& kv : c->dag) { cudaFree(kv.second.bulk); cudaFree(kv.second.chain); }
     cudaFree(c->wkSpill);
+    peer_release(c);
     cudaFree(c->eiVal); cudaFree(c->eiIdx);
     cudaFree(c->mcTheta); cudaFree(c->mcYerr2); cudaFree(c->mcLl); cudaFree(c->mcQ); cudaFree(c->mcInfo);
     cudaFree(c->mcKeys); cudaFree(c->mcOrder); cudaFree(c->mcBar);
@@ -270,6 +290,7 @@ static int dag_setup(fab_ctx* c, int B, int mode, size_t smem_limit, DagArgs* ou
     a.gd = gd; a.wk = c->wk; a.theta = nullptr; a.yerr2 = nullptr; a.ll = nullptr; a.info = nullptr; a.grad = nullptr;
     a.bulk = dv.bulk; a.chain = dv.chain; a.nbulk = dv.nbulk; a.nchain = dv.nchain;
     a.nslot = nslot; a.mode = mode; a.resident = resident; a.ntiles = ntiles; a.wk_spill = c->wkSpill;
+    a.peer.world = 0;
     *out = a;
     *smem_out = dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0);
     c->resident = false;
@@ -282,12 +303,21 @@ static int dag_setup(fab_ctx* c, int B, int mode, size_t smem_limit, DagArgs* ou
 
 // One launch of the fused kernel (one CTA per walker).
 static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info, double* grad,
-                      int mode) {
+                      int mode, bool exchange = false) {
     DagArgs a;
     size_t smem = 0;
     const int rc = dag_setup(c, B, mode, (size_t)c->smem_optin, &a, &smem);
     if (rc != FAB_OK) return rc;
     a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info; a.grad = grad;
+    if (exchange) {
+        const fab_ctx::Peer& p = c->peer;
+        const size_t parity = (size_t)(p.steps & 1ull) * p.buf_bytes;
+        for (int r = 0; r < p.world; ++r) {
+            a.peer.buf[r] = reinterpret_cast<double*>(static_cast<char*>(p.base[r]) + parity);
+            a.peer.cnt[r] = reinterpret_cast<unsigned*>(static_cast<char*>(p.base[r]) + peer_ctrl_offset(p));
+        }
+        a.peer.world = p.world; a.peer.rank = p.rank; a.peer.rows_per_rank = p.rows_per_rank; a.peer.row_doubles = p.row_doubles;
+    }
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     FAB_LAUNCH(gp_dag_kernel, B, DAG_THREADS, smem, c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
@@ -505,6 +535,104 @@ int fab_ei_batch(fab_ctx* c, const double* mu, const double* var, int B, int M, 
         FAB_LAUNCH(ei_argmax_final_kernel, B, 32, 0, c->stream, a, G, c->eiVal, c->eiIdx);
         FAB_CUDA(c, cudaGetLastError());
     }
+    return FAB_OK;
+}
+
+// ---- multi-GPU likelihood step with the exchange fused into the kernel (peer memory over NVLink / NVSwitch) ----
+int fab_peer_alloc(fab_ctx* c, int rank, int world, int rows_per_rank, void* handle_out) {
+    if (!c) return FAB_EINVAL;
+    if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
+    if (world < 1 || world > FAB_MAX_PEERS || rank < 0 || rank >= world || rows_per_rank < 1 || !handle_out)
+        return fail(c, FAB_EINVAL, "need 1 <= world <= 8, 0 <= rank < world, rows_per_rank >= 1");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    peer_release(c);
+    fab_ctx::Peer& p = c->peer;
+    p.world = world; p.rank = rank; p.rows_per_rank = rows_per_rank; p.row_doubles = c->gd.Pk + 3;
+    p.buf_bytes = (((size_t)world * rows_per_rank * p.row_doubles * sizeof(double)) + 255) / 256 * 256;
+    void* base = nullptr;
+    if (cudaMalloc(&base, 2 * p.buf_bytes + 256) != cudaSuccess) { cudaGetLastError(); p = fab_ctx::Peer(); return fail(c, FAB_ENOMEM, "peer buffer allocation failed"); }
+    p.base[rank] = base;
+    FAB_CUDA(c, cudaMemsetAsync(base, 0, 2 * p.buf_bytes + 256, c->stream));
+    FAB_CUDA(c, cudaStreamSynchronize(c->stream));         // peers may write as soon as they have the handle
+    memset(handle_out, 0, 64);
+#ifndef FAB_CUSIM
+    cudaIpcMemHandle_t h;
+    FAB_CUDA(c, cudaIpcGetMemHandle(&h, base));
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle_out, &h, 64);
+#endif
+    return FAB_OK;
+}
+
+int fab_peer_connect(fab_ctx* c, const void* handles) {
+    if (!c) return FAB_EINVAL;
+    fab_ctx::Peer& p = c->peer;
+    if (p.world < 1 || !p.base[p.rank]) return fail(c, FAB_ESTATE, "fab_peer_alloc has not been called");
+    if (!handles && p.world > 1) return fail(c, FAB_EINVAL, "null pointer");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+#ifndef FAB_CUSIM
+    for (int r = 0; r < p.world; ++r) {
+        if (r == p.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + 64 * r, 64);
+        FAB_CUDA(c, cudaIpcOpenMemHandle(&p.base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+#else
+    if (p.world > 1) return fail(c, FAB_EUNSUPPORTED, "the emulator has no peers");
+#endif
+    p.connected = true;
+    p.steps = 0;
+    return FAB_OK;
+}
+
+int fab_gp_loglik_exchange(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, double* grad,
+                           int* info) {
+    if (!c) return FAB_EINVAL;
+    if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
+    if (!c->peer.connected) return fail(c, FAB_ESTATE, "fab_peer_connect has not been called");
+    if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
+    if (B != c->peer.rows_per_rank) return fail(c, FAB_EINVAL, "B must equal the rows_per_rank given to fab_peer_alloc");
+    if (c->peer.row_doubles != c->gd.Pk + 3) return fail(c, FAB_ESTATE, "the data changed shape since fab_peer_alloc");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    const int rc = launch_dag(c, theta, yerr2, B, ll, info, grad, grad ? DAG_GRAD : DAG_LL, true);
+    if (rc != FAB_OK) return rc;
+    c->peer.steps += 1;
+    return FAB_OK;
+}
+
+int fab_peer_wait(fab_ctx* c, const double** gathered, int* rows, int* row_doubles) {
+    if (!c) return FAB_EINVAL;
+    fab_ctx::Peer& p = c->peer;
+    if (!p.connected || p.steps == 0) return fail(c, FAB_ESTATE, "no exchanged likelihood step is in flight");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    char* base = static_cast<char*>(p.base[p.rank]);
+    unsigned* cnt = reinterpret_cast<unsigned*>(base + peer_ctrl_offset(p));
+    int* err = reinterpret_cast<int*>(base + peer_ctrl_offset(p) + 128);
+    const unsigned expected = (unsigned)(p.steps * (unsigned long long)p.world * p.rows_per_rank);
+    FAB_LAUNCH(peer_wait_kernel, 1, 1, 0, c->stream, cnt, expected, err);
+    FAB_CUDA(c, cudaGetLastError());
+    if (gathered) *gathered = reinterpret_cast<const double*>(base + (size_t)((p.steps - 1) & 1ull) * p.buf_bytes);
+    if (rows) *rows = p.world * p.rows_per_rank;
+    if (row_doubles) *row_doubles = p.row_doubles;
+    return FAB_OK;
+}
+
+int fab_peer_error(fab_ctx* c) {          // synchronises: 1 if a wait timed out (a peer never delivered), else 0
+    if (!c) return FAB_EINVAL;
+    fab_ctx::Peer& p = c->peer;
+    if (!p.connected) return 0;
+    int e = 0;
+    FAB_CUDA(c, cudaMemcpyAsync(&e, static_cast<char*>(p.base[p.rank]) + peer_ctrl_offset(p) + 128, sizeof(int),
+                                cudaMemcpyDeviceToHost, c->stream));
+    FAB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return e;
+}
+
+int fab_peer_free(fab_ctx* c) {
+    if (!c) return FAB_EINVAL;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    peer_release(c);
     return FAB_OK;
 }
 

@@ -21,6 +21,17 @@ namespace fab {
 constexpr int DAG_BULK_THREADS = NTHREADS;         // warps 0..7
 constexpr int DAG_THREADS = NTHREADS + 32 * NCW;   // + the chain warps
 
+// Peer exchange of the per-walker results (multi-GPU likelihood step): instead of an
+// all-gather after the kernel, the CTA that finishes walker b stores its row [grad (Pk+1) | ll | info] straight
+// into the gather buffer of EVERY rank (NVLink / NVSwitch peer stores; the local rank is just another entry)
+// and then bumps every rank's arrival counter with a system-scope release.  world == 0: no exchange.
+constexpr int FAB_MAX_PEERS = 8;
+struct PeerTable {
+    double* buf[FAB_MAX_PEERS];        // this step's gather buffer of rank r (world x rows_per_rank x row_doubles)
+    unsigned* cnt[FAB_MAX_PEERS];      // arrival counter of rank r
+    int world, rank, rows_per_rank, row_doubles;
+};
+
 struct DagArgs {
     GpData gd;
     GpWork wk;
@@ -36,6 +47,7 @@ struct DagArgs {
     int resident;          // 1: scaled coordinates, z, accw, alpha of all Np rows live in shared memory
     int ntiles;            // NT (NT + 1) / 2: workspace tile indices >= ntiles address the spill region wk_spill
     double* wk_spill;      // B x NT tiles (FACTOR mode only: inverted diagonal tiles that had to leave shared memory)
+    PeerTable peer;
 };
 
 __host__ __device__ inline size_t dag_smem_bytes(int nslot, int d, int resident_np) {
@@ -564,9 +576,46 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             go[Pk] = bad ? NAN : 0.5 * gacc[MAX_PK];
         }
     }
+    if (a.peer.world > 0 && tid == 0) {
+        // the chain published ll / info before the acquire above; the gradient row was written by this thread
+        const int rd = a.peer.row_doubles;
+        const size_t row = ((size_t)a.peer.rank * a.peer.rows_per_rank + b) * rd;
+        const double llv = a.ll[b], infov = (double)a.info[b];
+        for (int r = 0; r < a.peer.world; ++r) {
+            double* dst = a.peer.buf[r] + row;
+            if (a.mode == DAG_GRAD && a.grad)
+                for (int q = 0; q <= Pk; ++q) dst[q] = a.grad[(size_t)b * (Pk + 1) + q];
+            dst[rd - 2] = llv;
+            dst[rd - 1] = infov;
+        }
+#ifndef FAB_CUSIM
+        __threadfence_system();
+        for (int r = 0; r < a.peer.world; ++r)
+            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.peer.cnt[r]) : "memory");
+#else
+        for (int r = 0; r < a.peer.world; ++r) *a.peer.cnt[r] += 1;
+#endif
+    }
     if (tid == 0) bulk_s2g_wait_all();
     PHE(51);
     PHE(40);
+}
+
+// Consumer side of the peer exchange: returns when `expected` rows have arrived in this rank's gather buffer
+// (acquire at system scope), or sets *err after ~2 s (a peer died): the launch never hangs the GPU.
+__global__ void peer_wait_kernel(unsigned* cnt, unsigned expected, int* err) {
+#ifndef FAB_CUSIM
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if ((int)(v - expected) >= 0) break;
+        if (clock64() - t0 > 4000000000LL) { *err = 1; break; }
+        __nanosleep(100);
+    }
+#else
+    if ((int)(*cnt - expected) < 0) *err = 1;
+#endif
 }
 
 // 12 warps: 65536 / 384 = 170 -> 168 registers per thread.

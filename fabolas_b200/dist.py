@@ -51,6 +51,14 @@ def sharded_loglik(engine, theta, yerr2, grad: bool = False):
     yerr2 = np.asarray(yerr2, dtype=np.float64).reshape(-1)
     B = theta.shape[0]
     lo, hi = shard_range(B, rank, size)
+    if size > 1 and getattr(engine, "peer_world", 0) == size and getattr(engine, "peer_rows", 0) == hi - lo \
+            and B == size * (hi - lo):
+        # exchange fused into the kernel (Engine.peer_setup was called): each CTA stores its walker's row into every
+        # rank's gather buffer over NVLink peer memory; no collective
+        engine.loglik_exchange(theta[lo:hi], yerr2[lo:hi], grad=grad)
+        rows = engine.peer_wait()
+        ll, info = rows[:, -2].contiguous(), rows[:, -1].to(torch.int32)
+        return (ll, rows[:, :-2].contiguous(), info) if grad else (ll, info)
     if hi > lo:
         out = engine.loglik(theta[lo:hi], yerr2[lo:hi], grad=grad)
     else:

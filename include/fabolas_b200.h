@@ -132,6 +132,28 @@ int fab_es_information_gain_batch(fab_ctx* ctx, const double* Xc, int M, double*
 int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta, int B, const double* Xa,
                       int Na, const double* Xb, int Nb, int D, double amp_mult, double* K, double* dK);
 
+/* Multi-GPU likelihood step with the exchange fused into the kernel (walkers sharded across
+ * the GPUs of one box, one process per GPU; the only exchange of the path is the all-gather of the per-walker
+ * log-likelihood (+ gradient) after every step -- the reference itself is single-process, fabolas.py:103-117).
+ * Instead of a collective after the kernel, the CTA that finishes a walker stores its result row straight into the
+ * gather buffer of EVERY rank through NVLink / NVSwitch peer memory and bumps every rank's arrival counter.
+ *   fab_peer_alloc    allocates this rank's buffers (two gather buffers by step parity, counter) and writes the
+ *                     64-byte CUDA IPC handle to handle_out (host); exchange the handles with any transport
+ *   fab_peer_connect  handles: world x 64 bytes (host, rank order); maps the peers' buffers
+ *   fab_gp_loglik_exchange  = fab_gp_loglik_batch on this rank's B = rows_per_rank walkers, plus the peer stores
+ *   fab_peer_wait     enqueues the wait for all world x B rows of the most recent exchanged step on the stream and
+ *                     returns the device pointer of this rank's gathered rows: rows x row_doubles, row of walker b of
+ *                     rank r at (r * B + b): [grad (Pk+1; only written when grad was requested) | ll | info]; valid for
+ *                     stream-ordered work until the next-but-one exchanged step
+ *   fab_peer_error    synchronises the stream; 1 if a wait gave up after ~2 s (a peer never delivered)          */
+int fab_peer_alloc(fab_ctx* ctx, int rank, int world, int rows_per_rank, void* handle_out);
+int fab_peer_connect(fab_ctx* ctx, const void* handles);
+int fab_gp_loglik_exchange(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll, double* grad,
+                           int* info);
+int fab_peer_wait(fab_ctx* ctx, const double** gathered, int* rows, int* row_doubles);
+int fab_peer_error(fab_ctx* ctx);
+int fab_peer_free(fab_ctx* ctx);
+
 /* emcee's EnsembleSampler(K, P, log_prob).run_mcmc(p0, nsteps) with the stretch move (a = 2, red/blue halves)
  * as the reference drives it (fabolas.py:103-117, entropy_search.py:80-85), with the reference's own
  * log-probability -- prior 0: fabolas.log_likelihood (fabolas.py:16-66, goes with FAB_FAMILY_M52_BASIS),

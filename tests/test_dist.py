@@ -54,3 +54,36 @@ def test_sharded_paths_world2_gloo():
     [p.start() for p in procs]
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs) and len(out) == 2
+
+
+def _check_exchange_world1(eng):
+    """The fused exchange with a world of one: the kernel's peer stores land in the local gather buffer."""
+    import torch
+    from fabolas_b200.workloads import gp_workload
+    w = gp_workload(1, n_walkers=6)
+    eng.set_data(w["family"], w["X"][:40], w["y"][:40], w["mean"], w["amp_mult"])
+    eng.peer_setup(6)
+    try:
+        for step, grad in enumerate((True, False, True)):
+            th = w["theta"] + 0.01 * step
+            ref = eng.loglik(th, w["yerr2"], grad=True)
+            out = eng.loglik_exchange(th, w["yerr2"], grad=grad)
+            rows = eng.peer_wait()
+            assert not eng.peer_error()
+            rows = rows.cpu().numpy() if rows.is_cuda else rows.numpy()
+            assert rows.shape == (6, eng.Pk + 3)
+            assert np.array_equal(rows[:, -2], ref[0].cpu().numpy()) and np.array_equal(rows[:, -1], ref[2].cpu().numpy())
+            assert np.array_equal(out[0].cpu().numpy(), ref[0].cpu().numpy())
+            if grad:
+                assert np.array_equal(rows[:, :-2], ref[1].cpu().numpy())
+    finally:
+        eng.peer_free()
+
+
+def test_fused_exchange_world1_emulated(sim_engine):
+    _check_exchange_world1(sim_engine)
+
+
+@pytest.mark.gpu
+def test_fused_exchange_world1_gpu(gpu_engine):
+    _check_exchange_world1(gpu_engine)
