@@ -122,7 +122,7 @@ void peer_release(fab_ctx* c) {
     if (c->peer.world > 0 && c->peer.base[c->peer.rank]) cudaFree(c->peer.base[c->peer.rank]);
     c->peer = fab_ctx::Peer();
 }
-inline size_t peer_ctrl_offset(const fab_ctx::Peer& p) { return 2 * p.buf_bytes; }     // counter, then error flag
+inline size_t peer_ctrl_offset(const fab_ctx::Peer& p) { return 2 * p.buf_bytes; }     // +0 arrivals, +64 local CTAs done, +128 error flag
 
 }  // namespace
 
@@ -316,6 +316,8 @@ static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int 
             a.peer.buf[r] = reinterpret_cast<double*>(static_cast<char*>(p.base[r]) + parity);
             a.peer.cnt[r] = reinterpret_cast<unsigned*>(static_cast<char*>(p.base[r]) + peer_ctrl_offset(p));
         }
+        a.peer.done = reinterpret_cast<unsigned*>(static_cast<char*>(p.base[p.rank]) + peer_ctrl_offset(p) + 64);
+        a.peer.done_target = (unsigned)((p.steps + 1) * (unsigned long long)B);
         a.peer.world = p.world; a.peer.rank = p.rank; a.peer.rows_per_rank = p.rows_per_rank; a.peer.row_doubles = p.row_doubles;
     }
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
@@ -608,7 +610,7 @@ int fab_peer_wait(fab_ctx* c, const double** gathered, int* rows, int* row_doubl
     char* base = static_cast<char*>(p.base[p.rank]);
     unsigned* cnt = reinterpret_cast<unsigned*>(base + peer_ctrl_offset(p));
     int* err = reinterpret_cast<int*>(base + peer_ctrl_offset(p) + 128);
-    const unsigned expected = (unsigned)(p.steps * (unsigned long long)p.world * p.rows_per_rank);
+    const unsigned expected = (unsigned)(p.steps * (unsigned long long)p.world);      // one signal per rank and step
     FAB_LAUNCH(peer_wait_kernel, 1, 1, 0, c->stream, cnt, expected, err);
     FAB_CUDA(c, cudaGetLastError());
     if (gathered) *gathered = reinterpret_cast<const double*>(base + (size_t)((p.steps - 1) & 1ull) * p.buf_bytes);

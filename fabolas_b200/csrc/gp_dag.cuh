@@ -22,13 +22,16 @@ constexpr int DAG_BULK_THREADS = NTHREADS;         // warps 0..7
 constexpr int DAG_THREADS = NTHREADS + 32 * NCW;   // + the chain warps
 
 // Peer exchange of the per-walker results (multi-GPU likelihood step): instead of an
-// all-gather after the kernel, the CTA that finishes walker b stores its row [grad (Pk+1) | ll | info] straight
-// into the gather buffer of EVERY rank (NVLink / NVSwitch peer stores; the local rank is just another entry)
-// and then bumps every rank's arrival counter with a system-scope release.  world == 0: no exchange.
+// all-gather after the kernel, the LAST CTA of the launch to finish (local completion counter) pushes this
+// rank's block of result rows [grad (Pk+1) | ll | info] straight into the gather buffer of EVERY rank (NVLink /
+// NVSwitch peer stores by all of its bulk threads; the local rank is just another entry), then one system-scope
+// fence and one arrival signal per rank.  world == 0: no exchange.
 constexpr int FAB_MAX_PEERS = 8;
 struct PeerTable {
     double* buf[FAB_MAX_PEERS];        // this step's gather buffer of rank r (world x rows_per_rank x row_doubles)
-    unsigned* cnt[FAB_MAX_PEERS];      // arrival counter of rank r
+    unsigned* cnt[FAB_MAX_PEERS];      // arrival counter of rank r (+1 per rank and step)
+    unsigned* done;                    // local: CTAs of this rank that have finished (monotonic over steps)
+    unsigned done_target;              // value of *done once every CTA of THIS step has finished
     int world, rank, rows_per_rank, row_doubles;
 };
 
@@ -54,6 +57,22 @@ __host__ __device__ inline size_t dag_smem_bytes(int nslot, int d, int resident_
     const size_t coords = resident_np ? (size_t)(d + 4) * resident_np : (size_t)(2 * (d + 1) * TS + 2 * TS);
     return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + EXP_TAB_N + 512 + 128 + 64 + 64 + 64 + 4 * TS) + 8 * coords +
            8 * MAX_SLOTS + 64;
+}
+
+// results of other CTAs of the same launch, read by the last CTA: past L1
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+#ifdef FAB_CUSIM
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ int ld_cg_i32(const int* p) {
+#ifdef FAB_CUSIM
+    return *p;
+#else
+    return __ldcg(p);
+#endif
 }
 
 // ---- stream synchronisation: completion counters in shared memory ----
@@ -576,25 +595,42 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             go[Pk] = bad ? NAN : 0.5 * gacc[MAX_PK];
         }
     }
-    if (a.peer.world > 0 && tid == 0) {
-        // the chain published ll / info before the acquire above; the gradient row was written by this thread
-        const int rd = a.peer.row_doubles;
-        const size_t row = ((size_t)a.peer.rank * a.peer.rows_per_rank + b) * rd;
-        const double llv = a.ll[b], infov = (double)a.info[b];
-        for (int r = 0; r < a.peer.world; ++r) {
-            double* dst = a.peer.buf[r] + row;
-            if (a.mode == DAG_GRAD && a.grad)
-                for (int q = 0; q <= Pk; ++q) dst[q] = a.grad[(size_t)b * (Pk + 1) + q];
-            dst[rd - 2] = llv;
-            dst[rd - 1] = infov;
-        }
-#ifndef FAB_CUSIM
-        __threadfence_system();
-        for (int r = 0; r < a.peer.world; ++r)
-            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.peer.cnt[r]) : "memory");
+    if (a.peer.world > 0) {
+        // this walker's ll / info (chain) and gradient row (thread 0) are in local memory; count the CTA in
+        named_bar_sync(1, DAG_BULK_THREADS);
+        if (tid == 0) {
+#ifdef FAB_CUSIM
+            const unsigned prev = *a.peer.done; *a.peer.done = prev + 1u;
 #else
-        for (int r = 0; r < a.peer.world; ++r) *a.peer.cnt[r] += 1;
+            __threadfence();
+            const unsigned prev = atomicAdd(a.peer.done, 1u);
+            __threadfence();
 #endif
+            sync[4] = (prev + 1u == a.peer.done_target) ? 1 : 0;
+        }
+        named_bar_sync(1, DAG_BULK_THREADS);
+        if (sync[4]) {                    // last CTA of this rank: every row of the block is final and visible
+            const int rd = a.peer.row_doubles, nB = a.peer.rows_per_rank;
+            const size_t base = (size_t)a.peer.rank * nB * rd;
+            for (int e = tid; e < nB * rd; e += DAG_BULK_THREADS) {
+                const int bb = e / rd, q = e - bb * rd;
+                double v;
+                if (q == rd - 2) v = ld_cg_f64(&a.ll[bb]);
+                else if (q == rd - 1) v = (double)ld_cg_i32(&a.info[bb]);
+                else v = (a.mode == DAG_GRAD && a.grad) ? ld_cg_f64(&a.grad[(size_t)bb * (Pk + 1) + q]) : 0.0;
+                for (int r = 0; r < a.peer.world; ++r) a.peer.buf[r][base + e] = v;
+            }
+            named_bar_sync(1, DAG_BULK_THREADS);
+            if (tid == 0) {
+#ifndef FAB_CUSIM
+                __threadfence_system();
+                for (int r = 0; r < a.peer.world; ++r)
+                    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(a.peer.cnt[r]) : "memory");
+#else
+                for (int r = 0; r < a.peer.world; ++r) *a.peer.cnt[r] += 1;
+#endif
+            }
+        }
     }
     if (tid == 0) bulk_s2g_wait_all();
     PHE(51);

@@ -143,7 +143,7 @@ int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta
  *   fab_gp_loglik_exchange  = fab_gp_loglik_batch on this rank's B = rows_per_rank walkers, plus the peer stores
  *   fab_peer_wait     enqueues the wait for all world x B rows of the most recent exchanged step on the stream and
  *                     returns the device pointer of this rank's gathered rows: rows x row_doubles, row of walker b of
- *                     rank r at (r * B + b): [grad (Pk+1; only written when grad was requested) | ll | info]; valid for
+ *                     rank r at (r * B + b): [grad (Pk+1; zero when grad was not requested) | ll | info]; valid for
  *                     stream-ordered work until the next-but-one exchanged step
  *   fab_peer_error    synchronises the stream; 1 if a wait gave up after ~2 s (a peer never delivered)          */
 int fab_peer_alloc(fab_ctx* ctx, int rank, int world, int rows_per_rank, void* handle_out);
