@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
     double* om = logU + Z;                                  // I x Z
     double* det = om + (size_t)I * Z;                       // Z
     double* sdm = det + Z;                                  // Z
-    double* red = sdm + Z;                                  // nw
+    double* red = sdm + Z;                                  // nw (8 reserved)
+    double* etab = red + 8;                                 // exp table of exp_neg_fast
+    exp_table_fill(etab);
     for (int e = tid; e < 8 * Z; e += ES_THREADS) coef[e] = a.st.coef[(size_t)b * 8 * Z + e];
     for (int e = tid; e < Z; e += ES_THREADS) logU[e] = a.st.logU[(size_t)b * Z + e];
     for (int e = tid; e < I * Z; e += ES_THREADS) om[e] = a.st.omega[(size_t)b * I * Z + e];
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
             double se = 0.0, sw = 0.0;
             for (int q = 0; q < Z; ++q) {
                 const double t = fma(sdm[q], o, det[q]);
-                const double e = exp_nonpos(t - mx);      // t <= mx; non-finite t makes the sums NaN -> nan_flag
+                const double e = exp_neg_fast(mx - t, etab);   // t <= mx; non-finite t makes the sums NaN -> nan_flag
                 se += e;
                 sw = fma(e, t, sw);
             }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
 }
 
 __host__ __device__ inline size_t es_entropy_smem_bytes(int Z, int I) {
-    return 8 * (size_t)(8 * Z + Z + I * Z + 2 * Z + 8) + 64;
+    return 8 * (size_t)(8 * Z + Z + I * Z + 2 * Z + 8 + EXP_TAB_N) + 64;
 }
 
 // grid (ceil(M / 128)): ig[x] = mean_b partial[x][b] in fixed order; NaN -> flag.

@@ -1,0 +1,68 @@
+"""One full FABOLAS candidate search (fabolas.get_candidate, fabolas.py:120-264) at the reference's own sizes --
+the svm_mnist prior (N = 100, D = 3), K = 20 hyper-samples, 100 + 500 MCMC steps, Z = 50 representers, I = 20
+innovations, L-BFGS-B to convergence -- timed phase by phase on the GPU engine, and, for scale, the CPU oracle's
+restatement of acquisitions.information_gain_cost timed on the host for a few evaluations of the same kind.
+    python tools/time_get_candidate.py"""
+import json, sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+from fabolas_b200 import fabolas as ff, acquisitions as fa
+from oracle import acq_oracle as ao, epmgp_oracle as eo, george_oracle as go
+
+g = np.load("tests/golden/gp_oracle_svm_mnist.npz")
+X = g["X"][:, :2]; s = 1 - np.sqrt(g["X"][:, 2])
+ds = lambda: {"X": X.copy(), "y": g["y"].copy(), "size": s.copy(), "c": np.log10(1 + 100 * s) + 0.5}
+bounds = [(-10, 10), (-10, 10), (1 / 256, 1)]
+
+calls = {"n": 0, "pts": 0}
+_orig = fa.information_gain_cost_batch
+def counted(pts, *a, **k):
+    calls["n"] += 1; calls["pts"] += len(np.atleast_2d(pts))
+    return _orig(pts, *a, **k)
+ff.information_gain_cost_batch = counted
+
+out = {}
+for rep in range(2):                       # first repetition warms up (library load, program upload, allocations)
+    np.random.seed(1)
+    calls.update(n=0, pts=0)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = ff.get_candidate(ds(), bounds, batched_fd=True)
+    torch.cuda.synchronize(); out["get_candidate_s"] = time.perf_counter() - t0
+out.update(x=[float(v) for v in r.x], fun=float(r.fun), lbfgs_iterations=int(r.nit), objective_calls=calls["n"],
+           information_gain_points=calls["pts"])
+# phases
+np.random.seed(1)
+d = ds()
+Xs = np.concatenate([d["X"], d["size"].reshape(-1, 1)], axis=1)
+Xf = np.concatenate((Xs[:, :-1], ((1 - Xs[:, -1]) ** 2).reshape(-1, 1)), axis=1)
+for name, fn in (("sample_hypers_device_s", lambda: ff.sample_hypers(Xf, d["y"], K=20)),
+                 ("sample_hypers_host_loop_s", lambda: ff.sample_hypers(Xf, d["y"], K=20, on_device=False))):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter(); h = fn(); torch.cuda.synchronize()
+    out[name] = time.perf_counter() - t0
+# CPU oracle: one information_gain_cost evaluation with the reference's algorithm (K = 20 models, Z = 50, I = 20)
+rng = np.random.default_rng(0)
+K, Z, I = 20, 50, 20
+theta, noise = ff._model_theta(h, 3)
+models, cmodels = [], []
+for b in range(K):
+    gp = go.GP(go.build_kernel(1, theta[b], 3), mean=float(d["y"].mean())); gp.compute(Xf, np.sqrt(noise[b])); models.append(gp)
+    gc = go.GP(go.build_kernel(1, theta[b], 3), mean=float(d["c"].mean())); gc.compute(Xs, np.sqrt(noise[b])); cmodels.append(gc)
+reps = rng.uniform([b[0] for b in bounds], [b[1] for b in bounds], (K, Z, 3))
+t0 = time.perf_counter()
+pmin, U = [], []
+for b in range(K):
+    mu, cov = models[b].predict(d["y"], reps[b], return_cov=True)
+    cov = np.clip(cov, np.finfo(float).eps, None)
+    pmin.append(eo.joint_min(mu, cov, with_derivatives=True))
+    U.append(np.clip(ao.expected_improvement(mu, cov, np.array([mu.max()])), np.finfo(float).eps, None))
+out["cpu_oracle_setup_predict_ei_epmgp_s"] = time.perf_counter() - t0
+Om = [[rng.standard_normal((Z, 1)) for _ in range(I)] for _ in range(K)]
+t0 = time.perf_counter()
+n_eval = 3
+for i in range(n_eval):
+    ao.information_gain_cost(np.array([0.5 * i, -1.0, 0.3]), cmodels, models, {"y": d["y"], "c": d["c"]}, pmin, list(reps), U, Om, n_innovations=I)
+out["cpu_oracle_information_gain_cost_s_per_eval"] = (time.perf_counter() - t0) / n_eval
+out["cpu_oracle_note"] = ("numpy restatement of acquisitions.information_gain_cost (C restatement of epmgp for the setup), one "
+                          "host thread pool as numpy uses it; the reference's L-BFGS-B needs (D+1) such evaluations per gradient")
+out["gpu_information_gain_cost_s_per_point"] = None
+print(json.dumps(out))
