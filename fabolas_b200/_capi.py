@@ -54,6 +54,12 @@ SIGNATURES = {
     "fab_peer_free": (_c_int, [_vp]),
     "fab_mcmc_run": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, ctypes.c_ulonglong,
                               ctypes.c_longlong, _c_dbl, _vp, _vp, _vp]),
+    "fab_mcmc_peer_alloc": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "fab_mcmc_peer_connect": (_c_int, [_vp, _vp]),
+    "fab_mcmc_peer_state": (_c_int, [_vp, _vp, _vp, _c_int]),
+    "fab_mcmc_run_sharded": (_c_int, [_vp, _c_int, _c_int, _c_int, ctypes.c_ulonglong, ctypes.c_longlong, _c_dbl, _vp]),
+    "fab_mcmc_peer_error": (_c_int, [_vp]),
+    "fab_mcmc_peer_free": (_c_int, [_vp]),
     "fab_mcmc_log_prior": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp]),
     "fab_ctx_debug_set_mcmc_ctas": (_c_int, [_vp, _c_int]),
     "fab_ctx_debug_set_max_slots": (_c_int, [_vp, _c_int]),
@@ -408,6 +414,55 @@ class Engine:
                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(iter0), float(a), _ptr(chain),
                                           _ptr(chain_lp), _ptr(nacc)), "fab_mcmc_run")
         return coords, lp, chain, chain_lp, nacc
+
+    def _exchange_handles(self, h, group):
+        """(rank, world, all handles as a ctypes buffer or None) for a 64-byte CUDA IPC handle of this rank."""
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if not multi:
+            return None
+        world = dist.get_world_size(group)
+        mine = torch.tensor(list(h), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        return (ctypes.c_ubyte * (64 * world))(*allh.cpu().tolist())
+
+    def mcmc_peer_setup(self, K: int, P: int, group=None):
+        """Replicas of a K-walker ensemble on every rank of `group` (default: the world), mapped into each other."""
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        rank, world = (dist.get_rank(group), dist.get_world_size(group)) if multi else (0, 1)
+        h = (ctypes.c_ubyte * 64)()
+        self._check(self.lib.fab_mcmc_peer_alloc(self._ctx, rank, world, int(K), int(P), ctypes.cast(h, _vp)), "fab_mcmc_peer_alloc")
+        buf = self._exchange_handles(h, group)
+        self._check(self.lib.fab_mcmc_peer_connect(self._ctx, None if buf is None else ctypes.cast(buf, _vp)), "fab_mcmc_peer_connect")
+        if multi:
+            dist.barrier(group=group)
+        self.mcmc_world, self.mcmc_rank, self.mcmc_K, self.mcmc_P = world, rank, int(K), int(P)
+
+    def mcmc_run_sharded(self, prior: int, coords, nsteps: int, log_prob=None, seed: int = 0, iter0: int = 0,
+                         a: float = 2.0, naccepted=None):
+        """mcmc_run with the walkers sharded over the ranks set up by mcmc_peer_setup; every rank passes the SAME
+        coords (and log_prob) and gets the same (coords, log_prob) back; naccepted counts this rank's proposals."""
+        coords = self.tensor(coords)
+        K, P = coords.shape
+        if (K, P) != (getattr(self, "mcmc_K", 0), getattr(self, "mcmc_P", 0)):
+            raise FabolasError("mcmc_peer_setup was made for a different ensemble shape")
+        init = log_prob is None
+        lp = self.empty(K) if init else self.tensor(log_prob)
+        nacc = torch.zeros(K, dtype=torch.int64, device=self.device) if naccepted is None else naccepted
+        self._check(self.lib.fab_mcmc_peer_state(self._ctx, _ptr(coords), None if init else _ptr(lp), 1), "fab_mcmc_peer_state")
+        self._check(self.lib.fab_mcmc_run_sharded(self._ctx, int(prior), int(nsteps), int(init), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                  int(iter0), float(a), _ptr(nacc)), "fab_mcmc_run_sharded")
+        self._check(self.lib.fab_mcmc_peer_state(self._ctx, _ptr(coords), _ptr(lp), 0), "fab_mcmc_peer_state")
+        return coords, lp, nacc
+
+    def mcmc_peer_error(self) -> bool:
+        return bool(self.lib.fab_mcmc_peer_error(self._ctx))
+
+    def mcmc_peer_free(self):
+        self.mcmc_world = self.mcmc_K = self.mcmc_P = 0
+        self._check(self.lib.fab_mcmc_peer_free(self._ctx), "fab_mcmc_peer_free")
 
     def log_prior(self, prior: int, params, want_theta: bool = False):
         """Log-prior of the reference's sampler log-probabilities for rows of walker positions (K, P)."""

@@ -58,6 +58,15 @@ struct fab_ctx {
         bool connected = false;
         unsigned long long steps = 0;
     } peer;
+    // sharded device sampler (mcmc.cuh): one IPC-exported allocation per rank holding the replica of coords (K x P)
+    // and lp (K), the barrier flag block and the error flag; the peers' mappings
+    struct McPeer {
+        int world = 0, rank = 0, K = 0, P = 0;
+        void* base[FAB_MAX_PEERS] = {nullptr};
+        bool connected = false;
+        unsigned xgen = 0;
+        size_t off_lp = 0, off_flag = 0, off_err = 0, bytes = 0;
+    } mpeer;
     // device-resident ensemble sampler (mcmc.cuh): per-CTA scratch records
     double* mcTheta = nullptr; double* mcYerr2 = nullptr; double* mcLl = nullptr; double* mcQ = nullptr;
     int* mcInfo = nullptr; unsigned long long* mcKeys = nullptr; int* mcOrder = nullptr; unsigned* mcBar = nullptr;
@@ -122,6 +131,14 @@ void peer_release(fab_ctx* c) {
     if (c->peer.world > 0 && c->peer.base[c->peer.rank]) cudaFree(c->peer.base[c->peer.rank]);
     c->peer = fab_ctx::Peer();
 }
+void mpeer_release(fab_ctx* c) {
+#ifndef FAB_CUSIM
+    for (int r = 0; r < c->mpeer.world; ++r)
+        if (r != c->mpeer.rank && c->mpeer.base[r]) cudaIpcCloseMemHandle(c->mpeer.base[r]);
+#endif
+    if (c->mpeer.world > 0 && c->mpeer.base[c->mpeer.rank]) cudaFree(c->mpeer.base[c->mpeer.rank]);
+    c->mpeer = fab_ctx::McPeer();
+}
 inline size_t peer_ctrl_offset(const fab_ctx::Peer& p) { return 2 * p.buf_bytes; }     // +0 arrivals, +64 local CTAs done, +128 error flag
 
 }  // namespace
@@ -168,6 +185,7 @@ int fab_ctx_destroy(fab_ctx* c) {
     for (auto& kv : c->dag) { cudaFree(kv.second.bulk); cudaFree(kv.second.chain); }
     cudaFree(c->wkSpill);
     peer_release(c);
+    mpeer_release(c);
     cudaFree(c->eiVal); cudaFree(c->eiIdx);
     cudaFree(c->mcTheta); cudaFree(c->mcYerr2); cudaFree(c->mcLl); cudaFree(c->mcQ); cudaFree(c->mcInfo);
     cudaFree(c->mcKeys); cudaFree(c->mcOrder); cudaFree(c->mcBar);
@@ -638,11 +656,11 @@ int fab_peer_free(fab_ctx* c) {
     return FAB_OK;
 }
 
-// The whole ensemble chain on the device: one persistent cooperative launch (mcmc.cuh).
-int fab_mcmc_run(fab_ctx* c, int prior, double* coords, double* log_prob, int K, int P, int nsteps, int init_lp,
-                 unsigned long long seed, long long iter0, double a_scale, double* chain, double* chain_lp,
-                 long long* naccepted) {
-    if (!c) return FAB_EINVAL;
+// The whole ensemble chain on the device: one persistent cooperative launch (mcmc.cuh).  `sharded`: coords / lp
+// are this rank's replica and the proposals are dealt to the ranks of the box.
+static int mcmc_launch(fab_ctx* c, int prior, double* coords, double* log_prob, int K, int P, int nsteps, int init_lp,
+                       unsigned long long seed, long long iter0, double a_scale, double* chain, double* chain_lp,
+                       long long* naccepted, bool sharded) {
     if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
     if (!coords || !log_prob || nsteps < 0 || !(a_scale > 1.0)) return fail(c, FAB_EINVAL, "bad argument");
     if (K < 2 || (K & 1)) return fail(c, FAB_EINVAL, "an even number of walkers >= 2 is required for the red/blue stretch move");
@@ -652,13 +670,15 @@ int fab_mcmc_run(fab_ctx* c, int prior, double* coords, double* log_prob, int K,
         return fail(c, FAB_EINVAL, "prior 0 (fabolas.py) goes with the basis-kernel family, prior 1 (entropy_search.py) with the Matern family");
     if (P != gd.Pk + 1) return fail(c, FAB_EINVAL, "walker dimension must be len(kernel) + 1 (the noise)");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    int grid = K / 2;
+    const int world = sharded ? c->mpeer.world : 1;
+    int grid = (K / 2 + world - 1) / world;     // proposals of a half-step that this rank owns
 #ifdef FAB_CUSIM
     grid = 1;                                   // the emulator runs CTAs one after the other: no grid barrier
 #else
     if (grid > c->num_sms) grid = c->num_sms;   // one CTA per SM (shared memory), all co-resident
 #endif
     if (c->mcmc_max_ctas > 0 && grid > c->mcmc_max_ctas) grid = c->mcmc_max_ctas;
+    if (grid < 1) grid = 1;
     McmcArgs m;
     size_t smem = 0;
     int rc = dag_setup(c, grid, DAG_LL, (size_t)c->smem_optin - MCMC_STATIC_SMEM, &m.dag, &smem);
@@ -677,6 +697,20 @@ int fab_mcmc_run(fab_ctx* c, int prior, double* coords, double* log_prob, int K,
     m.K = K; m.P = P; m.prior = prior; m.nsteps = nsteps; m.init_lp = init_lp != 0;
     m.seed = seed; m.iter0 = iter0; m.a = a_scale;
     m.chain = chain; m.chain_lp = chain_lp; m.nacc = naccepted; m.gbar = c->mcBar;
+    m.world = 1; m.rank = 0; m.xgen0 = 0; m.peer_err = nullptr;
+    for (int r = 0; r < FAB_MAX_PEERS; ++r) { m.peer_coords[r] = nullptr; m.peer_lp[r] = nullptr; m.peer_flag[r] = nullptr; }
+    if (sharded) {
+        fab_ctx::McPeer& p = c->mpeer;
+        m.world = p.world; m.rank = p.rank; m.xgen0 = p.xgen;
+        for (int r = 0; r < p.world; ++r) {
+            char* b = static_cast<char*>(p.base[r]);
+            m.peer_coords[r] = reinterpret_cast<double*>(b);
+            m.peer_lp[r] = reinterpret_cast<double*>(b + p.off_lp);
+            m.peer_flag[r] = reinterpret_cast<unsigned*>(b + p.off_flag);
+        }
+        m.peer_err = reinterpret_cast<int*>(static_cast<char*>(p.base[p.rank]) + p.off_err);
+        if (p.world > 1) p.xgen += 1u + (init_lp ? 1u : 0u) + 2u * (unsigned)nsteps;     // barriers of this launch
+    }
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
 #ifdef FAB_CUSIM
     FAB_LAUNCH(mcmc_stretch_kernel, grid, DAG_THREADS, smem, c->stream, m);
@@ -687,6 +721,104 @@ int fab_mcmc_run(fab_ctx* c, int prior, double* coords, double* log_prob, int K,
 #endif
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
+    return FAB_OK;
+}
+
+int fab_mcmc_run(fab_ctx* c, int prior, double* coords, double* log_prob, int K, int P, int nsteps, int init_lp,
+                 unsigned long long seed, long long iter0, double a_scale, double* chain, double* chain_lp,
+                 long long* naccepted) {
+    if (!c) return FAB_EINVAL;
+    return mcmc_launch(c, prior, coords, log_prob, K, P, nsteps, init_lp, seed, iter0, a_scale, chain, chain_lp, naccepted,
+                       false);
+}
+
+// ---- the same chain with the walkers sharded over the GPUs of one box ----
+int fab_mcmc_peer_alloc(fab_ctx* c, int rank, int world, int K, int P, void* handle_out) {
+    if (!c) return FAB_EINVAL;
+    if (world < 1 || world > FAB_MAX_PEERS || rank < 0 || rank >= world || K < 2 || P < 1 || !handle_out)
+        return fail(c, FAB_EINVAL, "need 1 <= world <= 8, 0 <= rank < world, K >= 2");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    mpeer_release(c);
+    fab_ctx::McPeer& p = c->mpeer;
+    p.world = world; p.rank = rank; p.K = K; p.P = P;
+    p.off_lp = (((size_t)K * P * sizeof(double)) + 255) / 256 * 256;
+    p.off_flag = p.off_lp + (((size_t)K * sizeof(double)) + 255) / 256 * 256;
+    p.off_err = p.off_flag + (size_t)FAB_MAX_PEERS * 64;
+    p.bytes = p.off_err + 256;
+    void* base = nullptr;
+    if (cudaMalloc(&base, p.bytes) != cudaSuccess) { cudaGetLastError(); p = fab_ctx::McPeer(); return fail(c, FAB_ENOMEM, "replica allocation failed"); }
+    p.base[rank] = base;
+    FAB_CUDA(c, cudaMemsetAsync(base, 0, p.bytes, c->stream));
+    FAB_CUDA(c, cudaStreamSynchronize(c->stream));
+    memset(handle_out, 0, 64);
+#ifndef FAB_CUSIM
+    cudaIpcMemHandle_t h;
+    FAB_CUDA(c, cudaIpcGetMemHandle(&h, base));
+    memcpy(handle_out, &h, 64);
+#endif
+    return FAB_OK;
+}
+
+int fab_mcmc_peer_connect(fab_ctx* c, const void* handles) {
+    if (!c) return FAB_EINVAL;
+    fab_ctx::McPeer& p = c->mpeer;
+    if (p.world < 1 || !p.base[p.rank]) return fail(c, FAB_ESTATE, "fab_mcmc_peer_alloc has not been called");
+    if (!handles && p.world > 1) return fail(c, FAB_EINVAL, "null pointer");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+#ifndef FAB_CUSIM
+    for (int r = 0; r < p.world; ++r) {
+        if (r == p.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + 64 * r, 64);
+        FAB_CUDA(c, cudaIpcOpenMemHandle(&p.base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+#else
+    if (p.world > 1) return fail(c, FAB_EUNSUPPORTED, "the emulator has no peers");
+#endif
+    p.connected = true;
+    p.xgen = 0;
+    return FAB_OK;
+}
+
+int fab_mcmc_peer_state(fab_ctx* c, double* coords, double* log_prob, int to_replica) {
+    if (!c) return FAB_EINVAL;
+    fab_ctx::McPeer& p = c->mpeer;
+    if (!p.connected) return fail(c, FAB_ESTATE, "fab_mcmc_peer_connect has not been called");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    char* b = static_cast<char*>(p.base[p.rank]);
+    const size_t nc = sizeof(double) * p.K * p.P, nl = sizeof(double) * p.K;
+    if (coords) FAB_CUDA(c, to_replica ? cudaMemcpyAsync(b, coords, nc, cudaMemcpyDeviceToDevice, c->stream)
+                                       : cudaMemcpyAsync(coords, b, nc, cudaMemcpyDeviceToDevice, c->stream));
+    if (log_prob) FAB_CUDA(c, to_replica ? cudaMemcpyAsync(b + p.off_lp, log_prob, nl, cudaMemcpyDeviceToDevice, c->stream)
+                                         : cudaMemcpyAsync(log_prob, b + p.off_lp, nl, cudaMemcpyDeviceToDevice, c->stream));
+    return FAB_OK;
+}
+
+int fab_mcmc_run_sharded(fab_ctx* c, int prior, int nsteps, int init_lp, unsigned long long seed, long long iter0,
+                         double a_scale, long long* naccepted) {
+    if (!c) return FAB_EINVAL;
+    fab_ctx::McPeer& p = c->mpeer;
+    if (!p.connected) return fail(c, FAB_ESTATE, "fab_mcmc_peer_connect has not been called");
+    char* b = static_cast<char*>(p.base[p.rank]);
+    return mcmc_launch(c, prior, reinterpret_cast<double*>(b), reinterpret_cast<double*>(b + p.off_lp), p.K, p.P, nsteps,
+                       init_lp, seed, iter0, a_scale, nullptr, nullptr, naccepted, true);
+}
+
+int fab_mcmc_peer_error(fab_ctx* c) {
+    if (!c) return FAB_EINVAL;
+    fab_ctx::McPeer& p = c->mpeer;
+    if (!p.connected) return 0;
+    int e = 0;
+    FAB_CUDA(c, cudaMemcpyAsync(&e, static_cast<char*>(p.base[p.rank]) + p.off_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FAB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return e;
+}
+
+int fab_mcmc_peer_free(fab_ctx* c) {
+    if (!c) return FAB_EINVAL;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    mpeer_release(c);
     return FAB_OK;
 }
 

@@ -42,6 +42,17 @@ struct McmcArgs {
     double* chain_lp;            // nsteps x K or null
     long long* nacc;             // K accepted-move counters (accumulated) or null
     unsigned* gbar;              // grid barrier counter, zero at launch
+    // ---- walkers sharded over the GPUs of one box (one process per GPU; world <= 1: single GPU) ----
+    // Every rank holds a replica of coords / lp inside a CUDA-IPC exported buffer; `coords` / `lp` above are this
+    // rank's replica.  Proposal positions are dealt round-robin to the ranks; the owner of an accepted move stores
+    // the new row into EVERY replica over NVLink peer memory, and the per-half-step barrier spans the box: local
+    // grid barrier, one flag store per peer after a system-scope fence, wait for every peer's flag, release.
+    double* peer_coords[FAB_MAX_PEERS];
+    double* peer_lp[FAB_MAX_PEERS];
+    unsigned* peer_flag[FAB_MAX_PEERS];   // flag block of rank r: generation reached by source rank q at [16 q]
+    int* peer_err;               // local: set when a peer did not show up within ~2 s
+    unsigned xgen0;              // cross-GPU barrier generations used by earlier launches
+    int world, rank;
 };
 
 struct Philox4 { unsigned x, y, z, w; };
@@ -149,6 +160,35 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 #endif
 }
 
+// Barrier over every CTA of every rank.  Remote stores issued by any thread of this rank before the barrier are
+// visible to every thread of every rank after it (block barrier -> gpu-scope release/acquire -> system-scope
+// fence and flag -> acquire on the peer -> its grid barrier).
+__device__ __forceinline__ void box_barrier(const McmcArgs& m, unsigned& gen, unsigned& xgen) {
+    grid_barrier(m.gbar, ++gen);
+    if (m.world > 1) {
+        ++xgen;
+#ifndef FAB_CUSIM
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            __threadfence_system();
+            for (int r = 0; r < m.world; ++r)
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(m.peer_flag[r] + 16 * m.rank), "r"(xgen) : "memory");
+            const long long t0 = clock64();
+            for (int r = 0; r < m.world; ++r) {
+                const unsigned* f = m.peer_flag[m.rank] + 16 * r;
+                for (;;) {
+                    unsigned v;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    if ((int)(v - xgen) >= 0) break;
+                    if (clock64() - t0 > 4000000000LL) { *m.peer_err = 1; break; }
+                    __nanosleep(64);
+                }
+            }
+        }
+#endif
+        grid_barrier(m.gbar, ++gen);
+    }
+}
+
 // Evaluate the log-probability of the P-vector in m.q (this CTA's record): thread 0 decodes the prior, the whole
 // CTA runs the likelihood.  Result valid in thread 0.
 __device__ __forceinline__ double mcmc_log_prob(const McmcArgs& m, unsigned char* smem_raw, unsigned& phases, bool& first,
@@ -183,19 +223,26 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
     const int K = m.K, P = m.P, half = K / 2;
     unsigned phases = 0u;
     bool first = true;
-    unsigned gen = 0;
+    unsigned gen = 0, xgen = m.xgen0;
+    const int W = m.world > 1 ? m.world : 1, R = m.world > 1 ? m.rank : 0;
     double* q = m.q + (size_t)cta * P;
     unsigned long long* keys = m.keys + (size_t)cta * K;
     int* order = m.order + (size_t)cta * K;
 
+    // every rank's kernel is running: whatever its stream did before (initial state, copies of the last chain) is done
+    if (m.world > 1) box_barrier(m, gen, xgen);
+
     if (m.init_lp) {                              // emcee: state.log_prob = compute_log_prob(coords) when not given
-        for (int i = cta; i < K; i += gridDim.x) {
+        for (int i = cta * W + R; i < K; i += gridDim.x * W) {
             if (tid < P) q[tid] = ld_cg(&m.coords[(size_t)i * P + tid]);
             __syncthreads();
             const double v = mcmc_log_prob(m, smem_raw, phases, first, flag);
-            if (tid == 0) m.lp[i] = v;
+            if (tid == 0) {
+                if (m.world > 1) { for (int r = 0; r < W; ++r) m.peer_lp[r][i] = v; }
+                else m.lp[i] = v;
+            }
         }
-        grid_barrier(m.gbar, ++gen);
+        box_barrier(m, gen, xgen);
     }
 
     for (int step = 0; step < m.nsteps; ++step) {
@@ -212,7 +259,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
         }
         __syncthreads();
         for (int split = 0; split < 2; ++split) {
-            for (int mm = cta; mm < half; mm += gridDim.x) {
+            for (int mm = cta * W + R; mm < half; mm += gridDim.x * W) {
                 const int s = order[split * half + mm];
                 double zfac = 0.0;
                 if (tid == 0) {
@@ -236,9 +283,16 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
                     const Philox4 r = mcmc_rand(m.seed, iter, 3 + split, mm);
                     const bool acc = lnpdiff > log(uniform53(r.x, r.y));
                     if (acc) {
-                        for (int k = 0; k < P; ++k) m.coords[(size_t)s * P + k] = q[k];
-                        m.lp[s] = new_lp;
-                        if (m.nacc) m.nacc[s] += 1;
+                        if (m.world > 1) {                                  // every replica, this rank's included
+                            for (int r = 0; r < W; ++r) {
+                                for (int k = 0; k < P; ++k) m.peer_coords[r][(size_t)s * P + k] = q[k];
+                                m.peer_lp[r][s] = new_lp;
+                            }
+                        } else {
+                            for (int k = 0; k < P; ++k) m.coords[(size_t)s * P + k] = q[k];
+                            m.lp[s] = new_lp;
+                        }
+                        if (m.nacc) m.nacc[s] += 1;                         // counted on the owning rank
                     }
                     if (split == 1 && (m.chain || m.chain_lp)) {
                         // after the second half-step: record this walker and the first-half walker of the same rank
@@ -256,7 +310,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
                     }
                 }
             }
-            grid_barrier(m.gbar, ++gen);
+            box_barrier(m, gen, xgen);
         }
     }
 }

@@ -125,9 +125,20 @@ class DeviceEnsembleSampler:
                                     else np.array(coords, dtype=np.float64, copy=True))
         if tuple(coords.shape) != (self.nwalkers, self.ndim):
             raise ValueError("incompatible input dimensions")
-        coords, lp, chain, chain_lp, nacc = self.engine.mcmc_run(
-            self.prior, coords, nsteps, log_prob=lp, seed=self.seed, iter0=self._steps_taken, a=self.a,
-            store_chain=store, naccepted=self._nacc)
+        sharded = (getattr(self.engine, "mcmc_world", 0) > 1 and getattr(self.engine, "mcmc_K", 0) == self.nwalkers
+                   and getattr(self.engine, "mcmc_P", 0) == self.ndim)
+        if sharded:
+            # walkers dealt to the GPUs of the box (Engine.mcmc_peer_setup was called on every rank; every rank passes
+            # the same state and the same seed); the chain itself is not recorded in this mode
+            if store:
+                raise ValueError("the sharded device sampler does not record the chain: call run_mcmc(..., store=False)")
+            coords, lp, nacc = self.engine.mcmc_run_sharded(self.prior, coords, nsteps, log_prob=lp, seed=self.seed,
+                                                            iter0=self._steps_taken, a=self.a, naccepted=self._nacc)
+            chain = chain_lp = None
+        else:
+            coords, lp, chain, chain_lp, nacc = self.engine.mcmc_run(
+                self.prior, coords, nsteps, log_prob=lp, seed=self.seed, iter0=self._steps_taken, a=self.a,
+                store_chain=store, naccepted=self._nacc)
         self._steps_taken += nsteps
         self.iteration += nsteps
         self._nacc = nacc

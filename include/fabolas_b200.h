@@ -172,6 +172,24 @@ int fab_mcmc_run(fab_ctx* ctx, int prior, double* coords, double* log_prob, int 
                  unsigned long long seed, long long iter0, double a, double* chain, double* chain_lp,
                  long long* naccepted);
 
+/* The same chain with the walkers sharded over the GPUs of one box (one process per GPU; SURVEY.md section 8e,
+ * BASELINE configs[4]).  Every rank holds a replica of the ensemble (coords K x P, log_prob K) in a CUDA-IPC exported
+ * buffer: fab_mcmc_peer_alloc writes the 64-byte handle to handle_out (host), fab_mcmc_peer_connect takes all
+ * world x 64 bytes in rank order.  fab_mcmc_peer_state copies the ensemble into (to_replica = 1: the SAME state on
+ * every rank) or out of (0) this rank's replica.  fab_mcmc_run_sharded is fab_mcmc_run on the replicas (every rank
+ * calls it with the same arguments): the proposals of a half-step are dealt round-robin to the ranks, the owner of
+ * an accepted move stores the new row into every replica over NVLink / NVSwitch peer memory, and the per-half-step
+ * barrier spans the box (flag stores after a system-scope fence; no collective, no host round trip).  The chain is
+ * bit-identical to fab_mcmc_run with the same seed.  naccepted counts on the owning rank only.
+ * fab_mcmc_peer_error synchronises: 1 if a barrier gave up after ~2 s (a peer never arrived).                   */
+int fab_mcmc_peer_alloc(fab_ctx* ctx, int rank, int world, int K, int P, void* handle_out);
+int fab_mcmc_peer_connect(fab_ctx* ctx, const void* handles);
+int fab_mcmc_peer_state(fab_ctx* ctx, double* coords, double* log_prob, int to_replica);
+int fab_mcmc_run_sharded(fab_ctx* ctx, int prior, int nsteps, int init_lp, unsigned long long seed, long long iter0,
+                         double a, long long* naccepted);
+int fab_mcmc_peer_error(fab_ctx* ctx);
+int fab_mcmc_peer_free(fab_ctx* ctx);
+
 /* The log-prior part of those two log-probabilities for K rows p (K x P), and the george parameter vector
  * (K x (P-1), may be NULL) and yerr^2 (K, may be NULL) their likelihood is evaluated at; -inf outside the
  * support (theta row then zero).  horseshoe.py:10-33 with scipy.special.exp1's algorithm, lognorm(s=1).       */

@@ -204,3 +204,29 @@ def test_sample_hypers_surface_emulated(sim_engine):
         assert h.shape == (4, 6) and np.all(np.isfinite(h)) and np.all((h[:, 0] > 0) & (h[:, 0] < 20))
         h = entropy_search.sample_hypers(X, y, K=4, burn_in=1, iterations=2, engine=sim_engine, on_device=on_device)
         assert h.shape == (4, 5) and np.all((h[:, -1] >= 0) & (h[:, -1] < 20))
+
+
+def _check_sharded_world1(eng):
+    """The sharded entry points with a world of one: same chain as fab_mcmc_run, state carried in the replica."""
+    X, y = _problem(22, 3, 1, seed=6)
+    eng.set_data(1, X, y, float(y.mean()), 3)
+    p0 = np.random.default_rng(3).uniform(0, 1, (6, 6))
+    ref_c, ref_lp, _, _, ref_n = eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.copy(), 5, seed=8, store_chain=False)
+    eng.mcmc_peer_setup(6, 6)
+    try:
+        c, lp, n = eng.mcmc_run_sharded(FAB_PRIOR_FABOLAS, p0.copy(), 2, seed=8)
+        c, lp, n = eng.mcmc_run_sharded(FAB_PRIOR_FABOLAS, c, 3, log_prob=lp, seed=8, iter0=2, naccepted=n)
+        assert not eng.mcmc_peer_error()
+        assert np.array_equal(c.cpu().numpy(), ref_c.cpu().numpy()) and np.array_equal(lp.cpu().numpy(), ref_lp.cpu().numpy())
+        assert np.array_equal(n.cpu().numpy(), ref_n.cpu().numpy())
+    finally:
+        eng.mcmc_peer_free()
+
+
+def test_sharded_sampler_world1_emulated(sim_engine):
+    _check_sharded_world1(sim_engine)
+
+
+@pytest.mark.gpu
+def test_sharded_sampler_world1_gpu(gpu_engine):
+    _check_sharded_world1(gpu_engine)
