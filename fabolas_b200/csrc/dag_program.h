@@ -43,7 +43,11 @@ enum DagOpFlags {
     DOPF_LAST = 2,        // last product of a K^-1 tile: contraction
     DOPF_WAIT_READ = 4,   // a slot that is the source of an earlier bulk store is overwritten from here on
     DOPF_DRAIN = 8,       // a tile loaded here was stored since the last drain: wait for all bulk stores first
-    DOPF_INPLACE = 16     // PUT over the partial tile P(I,J) that the preceding GET picked up (same slot)
+    DOPF_INPLACE = 16,    // PUT over the partial tile P(I,J) that the preceding GET picked up (same slot)
+    // PUT and GET do not run as ops of their own: they ride on the op that produces / continues the accumulators
+    DOPF_GET_BEFORE = 32, // acc = slot C (partial tile P(I,J)) before the op's own work
+    DOPF_PUT_AFTER = 64,  // slot C = acc after the op's own work; put_kind = kind of the tile (U, P or T)
+    DOPF_PUT_BARRIER = 128 // slot C is an operand slot of this very op (no other slot was free): the bulk warps meet first
 };
 constexpr int DAG_MAX_LOADS = 6;
 constexpr int DAG_PREFETCH_DEPTH = 3;
@@ -58,7 +62,8 @@ struct DagOp {             // 28 ints, read by every thread of its stream
     int nload;
     int ld_slot[DAG_MAX_LOADS];
     int ld_tile[DAG_MAX_LOADS];
-    int pad[3];
+    int put_kind;          // DOPF_PUT_AFTER: TK_U / TK_P / TK_T
+    int pad[2];
 };
 
 static_assert(sizeof(DagOp) == 112, "DagOp is read as int4 words by the kernel");
@@ -109,6 +114,10 @@ struct SymOp {            // one op before slot assignment
     int out;              // new tile id produced into a fresh slot (-1 none)
     double t;             // estimated start
     int idx;              // index within its stream
+    int get_in;           // DOPF_GET_BEFORE: partial tile picked up first (-1 none)
+    int put_out;          // DOPF_PUT_AFTER: tile id put into a fresh slot (-1: none or in place)
+    int put_inplace, put_inplace_to;   // DOPF_PUT_AFTER | DOPF_INPLACE: over the slot of the partial tile
+    int put_kind;
 };
 
 }  // namespace dagdetail
@@ -275,10 +284,24 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
 
     // ---- expand into symbolic ops with estimated start times ----
     std::vector<SymOp> ops;
+    int pending_get = -1;                      // partial tile a GET wants: rides on the next op pushed
+    double pending_get_t = 0.0;
     auto push = [&](int stream, int type, int I, int J, int k, int flags, int in0, int in1, int inpl, int inpl_to, int out,
                     double t) {
         SymOp o; o.stream = stream; o.type = type; o.I = I; o.J = J; o.k = k; o.flags = flags; o.in[0] = in0; o.in[1] = in1;
         o.inplace = inpl; o.inplace_to = inpl_to; o.out = out; o.t = t; o.idx = -1;
+        o.get_in = -1; o.put_out = -1; o.put_inplace = -1; o.put_inplace_to = -1; o.put_kind = -1;
+        if (type == DOP_GET) { pending_get = in0; pending_get_t = t; return; }
+        if (type == DOP_PUT) {                 // rides on the op that has just produced the accumulators
+            SymOp& p = ops.back();
+            p.flags |= DOPF_PUT_AFTER | (flags & DOPF_INPLACE);
+            p.put_kind = k; p.put_out = out; p.put_inplace = inpl; p.put_inplace_to = inpl_to;
+            return;
+        }
+        if (pending_get >= 0 && stream == 0) {
+            o.flags |= DOPF_GET_BEFORE; o.get_in = pending_get; o.t = pending_get_t;
+            pending_get = -1;
+        }
         ops.push_back(o);
     };
     for (int s = 0; s < 2; ++s)
@@ -348,6 +371,8 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
         const SymOp& o = ops[seq[g]];
         for (int q = 0; q < 2; ++q) if (o.in[q] >= 0) uses[o.in[q]].push_back((int)g);
         if (o.inplace >= 0) uses[o.inplace].push_back((int)g);
+        if (o.get_in >= 0) uses[o.get_in].push_back((int)g);
+        if (o.put_inplace >= 0) uses[o.put_inplace].push_back((int)g);
     }
     auto next_use = [&](int tile, int after) {
         auto it = uses.find(tile);
@@ -372,7 +397,7 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
         for (const SymOp& o : ops) {
             DagOp& d = prog[o.stream][o.idx];
             d.type = o.type; d.I = o.I; d.J = o.J; d.k = o.k; d.flags = o.flags;
-            d.slotA = d.slotB = d.slotC = -1; d.st_slot = d.st_tile = -1;
+            d.slotA = d.slotB = d.slotC = -1; d.st_slot = d.st_tile = -1; d.put_kind = o.put_kind;
         }
         struct Slot { int id = -1; bool clean = false; int lastB = -1, lastC = -1, storeB = -1; };
         std::vector<Slot> S(nslot);
@@ -452,7 +477,7 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
                 if (q < 0) { failed = true; P.err = "no evictable slot"; return 0; }
                 Load l;
                 l.slot = q; l.tile = ws_index(tile, mode, NT); l.needed_at = o.idx;
-                l.free_from = std::max(S[q].lastB + 1, stored_at[tile]);
+                l.free_from = std::max(S[q].lastB + 1, stored_at[tile] + 1);     // an op issues its loads before its store
                 l.min_chain = S[q].lastC; l.stored_at = stored_at[tile]; l.after_store = S[q].storeB >= 0;
                 if (S[q].storeB >= 0) l.free_from = std::max(l.free_from, S[q].storeB + 1);
                 if (S[q].lastC >= 0) {     // do not make the bulk stream wait for the chain earlier than the schedule expects
@@ -481,6 +506,12 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
                 S[p.slot].lastC = -1;                 // ordered through this op's wait from here on
                 stored_at[p.tile_id] = o.idx;
                 busy |= 1u << p.slot;                 // the store reads the slot during this very op
+            }
+            if (o.flags & DOPF_GET_BEFORE) {
+                const int q = find(o.get_in);
+                if (q < 0) { failed = true; P.err = "partial tile lost"; break; }
+                touch(q);
+                d.slotC = q;
             }
             switch (o.type) {
             case DOP_BUILD: break;
@@ -548,6 +579,28 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
                 break;
             }
             default: break;
+            }
+            if (!failed && (o.flags & DOPF_PUT_AFTER)) {
+                if (o.put_inplace >= 0) {                   // over the partial tile this op (or an earlier one) picked up
+                    const int q = find(o.put_inplace);
+                    if (q < 0) { failed = true; P.err = "partial tile lost"; break; }
+                    touch(q);
+                    S[q].id = o.put_inplace_to; S[q].clean = false;
+                    d.slotC = q;
+                } else {
+                    int q = victim(false);                  // not one of this op's operand slots (busy) ...
+                    if (q < 0) {                            // ... unless nothing else is free: then after a barrier
+                        const unsigned keep = busy;
+                        if (d.slotA >= 0) busy &= ~(1u << d.slotA);
+                        if (d.slotB >= 0) busy &= ~(1u << d.slotB);
+                        q = victim(false);
+                        busy = keep;
+                        if (q >= 0) d.flags |= DOPF_PUT_BARRIER;
+                    }
+                    if (q < 0) { failed = true; P.err = "no slot for an unfinished tile"; break; }
+                    overwrite(q, o.put_out, false);
+                    d.slotC = q;
+                }
             }
         }
         if (failed) return P;
@@ -626,6 +679,12 @@ inline std::string dag_verify(const DagProgram& P) {
         const DagOp& d = P.bulk[i];
         for (int q = 0; q < d.nload; ++q) rec(d.ld_slot[q], 0, i, true);
         if (d.st_slot >= 0) rec(d.st_slot, 0, i, false);
+        if (d.flags & DOPF_GET_BEFORE) rec(d.slotC, 0, i, false);
+        if (d.flags & DOPF_PUT_AFTER) {
+            rec(d.slotC, 0, i, true);
+            if ((d.slotC == d.slotA || d.slotC == d.slotB) && !(d.flags & DOPF_PUT_BARRIER))
+                return "a fused PUT targets an operand slot of its own op without a barrier";
+        }
         switch (d.type) {
         case DOP_MMA_NT: case DOP_P1_MMA: case DOP_P2_MMA: rec(d.slotA, 0, i, false); rec(d.slotB, 0, i, false); break;
         case DOP_PUT: rec(d.slotC, 0, i, true); break;
@@ -705,6 +764,10 @@ inline std::string dag_verify(const DagProgram& P) {
                 ws[d.st_tile] = content[d.st_slot]; store_unread[d.st_slot] = 1;
             }
             const int I = d.I, J = d.J, k = d.k;
+            if (d.flags & DOPF_GET_BEFORE) {
+                if (!(e = expect(d.slotC, tid_of(TK_P, I, J), "get", 0, ib)).empty()) return e;
+                acc_owner = tid_of(TK_U, I, J);
+            }
             switch (d.type) {
             case DOP_MMA_NT:
                 if (acc_owner != tid_of(TK_U, I, J)) { snprintf(buf, sizeof buf, "bulk op %d updates accumulators that belong to another tile", ib); return buf; }
@@ -749,6 +812,14 @@ inline std::string dag_verify(const DagProgram& P) {
                 if (!(e = expect(d.slotB, tid_of(TK_W, k, J), "B", 0, ib)).empty()) return e;
                 break;
             default: break;
+            }
+            if (d.flags & DOPF_PUT_AFTER) {
+                const int pk = d.put_kind;
+                if (acc_owner != tid_of(pk == TK_T ? TK_T : TK_U, I, J)) { snprintf(buf, sizeof buf, "bulk op %d puts accumulators that belong to another tile", ib); return buf; }
+                if (d.flags & DOPF_INPLACE) { if (!(e = expect(d.slotC, tid_of(TK_P, I, J), "put over", 0, ib)).empty()) return e; }
+                else if (!(e = clobber(d.slotC, "put", 0, ib)).empty()) return e;
+                content[d.slotC] = tid_of(pk, I, J);
+                acc_owner = -1;
             }
             ++ib; progressed = true;
         }

@@ -464,6 +464,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         const double* uc_p = a.resident ? us_all + TS * J : sl_c + d * TS;
         const int ldz = a.resident ? Np : TS;
 
+        if (flags & DOPF_GET_BEFORE) acc_load(acc, C, wt);      // partial tile P(I,J) continues in the accumulators
         switch (type) {
         case DOP_BUILD: {
 #define FAB_BUILD_ACC(DD) case DD: build_acc<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab); break;
@@ -562,6 +563,11 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             }
             break;
         default: break;
+        }
+        if (flags & DOPF_PUT_AFTER) {         // the tile leaves the accumulators: slot C is no operand of this op ...
+            if (flags & DOPF_PUT_BARRIER) named_bar_sync(1, DAG_BULK_THREADS);     // ... or everybody is done reading it
+            acc_store(acc, C, wt);
+            fence_proxy_async();
         }
         PHE(42 + type);
         TRB(i, 2);
