@@ -341,17 +341,11 @@ class Engine:
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         rank, world = (dist.get_rank(group), dist.get_world_size(group)) if multi else (0, 1)
         h = (ctypes.c_ubyte * 64)()
-        self._check(self.lib.fab_peer_alloc(self._ctx, rank, world, int(rows_per_rank), ctypes.cast(h, _vp)),
-                    "fab_peer_alloc")
-        if multi:
-            mine = torch.tensor(list(h), dtype=torch.uint8, device=self.device)
-            allh = torch.empty(world * 64, dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(allh, mine, group=group)
-            buf = (ctypes.c_ubyte * (64 * world))(*allh.cpu().tolist())
-            self._check(self.lib.fab_peer_connect(self._ctx, ctypes.cast(buf, _vp)), "fab_peer_connect")
-            dist.barrier(group=group)
-        else:
-            self._check(self.lib.fab_peer_connect(self._ctx, None), "fab_peer_connect")
+        rc = self.lib.fab_peer_alloc(self._ctx, rank, world, int(rows_per_rank), ctypes.cast(h, _vp))
+        buf = self._exchange_handles(h, group)                # every rank takes part, whatever its own outcome
+        if rc == 0:
+            rc = self.lib.fab_peer_connect(self._ctx, None if buf is None else ctypes.cast(buf, _vp))
+        self._agree(rc, "fab_peer_alloc / fab_peer_connect", group, self.lib.fab_peer_free)
         self._peer_views = {}
         self.peer_world, self.peer_rank, self.peer_rows = world, rank, int(rows_per_rank)
 
@@ -427,17 +421,32 @@ class Engine:
         dist.all_gather_into_tensor(allh, mine, group=group)
         return (ctypes.c_ubyte * (64 * world))(*allh.cpu().tolist())
 
+    def _agree(self, rc: int, what: str, group, undo):
+        """Every rank learns whether every rank mapped its peers (a rank that failed must not leave the others in a
+        collective): all succeed, or all release what they mapped and raise."""
+        import torch.distributed as dist
+        msg = self.lib.fab_last_error(self._ctx).decode() if rc != 0 else ""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            ok = torch.tensor([1.0 if rc == 0 else 0.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0.0:
+                undo(self._ctx)
+                raise FabolasError(f"{what} failed on at least one rank" + (f" (this rank: {rc}: {msg})" if rc != 0 else ""))
+        elif rc != 0:
+            undo(self._ctx)
+            raise FabolasError(f"{what} failed ({rc}): {msg}")
+
     def mcmc_peer_setup(self, K: int, P: int, group=None):
         """Replicas of a K-walker ensemble on every rank of `group` (default: the world), mapped into each other."""
         import torch.distributed as dist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         rank, world = (dist.get_rank(group), dist.get_world_size(group)) if multi else (0, 1)
         h = (ctypes.c_ubyte * 64)()
-        self._check(self.lib.fab_mcmc_peer_alloc(self._ctx, rank, world, int(K), int(P), ctypes.cast(h, _vp)), "fab_mcmc_peer_alloc")
-        buf = self._exchange_handles(h, group)
-        self._check(self.lib.fab_mcmc_peer_connect(self._ctx, None if buf is None else ctypes.cast(buf, _vp)), "fab_mcmc_peer_connect")
-        if multi:
-            dist.barrier(group=group)
+        rc = self.lib.fab_mcmc_peer_alloc(self._ctx, rank, world, int(K), int(P), ctypes.cast(h, _vp))
+        buf = self._exchange_handles(h, group)                # every rank takes part, whatever its own outcome
+        if rc == 0:
+            rc = self.lib.fab_mcmc_peer_connect(self._ctx, None if buf is None else ctypes.cast(buf, _vp))
+        self._agree(rc, "fab_mcmc_peer_alloc / fab_mcmc_peer_connect", group, self.lib.fab_mcmc_peer_free)
         self.mcmc_world, self.mcmc_rank, self.mcmc_K, self.mcmc_P = world, rank, int(K), int(P)
 
     def mcmc_run_sharded(self, prior: int, coords, nsteps: int, log_prob=None, seed: int = 0, iter0: int = 0,
