@@ -179,22 +179,31 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
             sdm[tid] = s * (c0 * coef[6 * Z + tid] + coef[7 * Z + tid]);
         }
         __syncthreads();
-        // one (innovation p, column bb) pair per thread pass: I * Z columns over the whole CTA
+        // two (innovation p, column bb) pairs per thread and pass (they share the det / sdm broadcasts and give the
+        // exp chains a partner to overlap with): I * Z columns over the whole CTA
         double acc = 0.0;
-        for (int c = tid; c < I * Z; c += ES_THREADS) {
-            const int bb = c % Z;
-            const double o = om[c];                       // om[p * Z + bb]
-            double mx = -INFINITY;
-            for (int q = 0; q < Z; ++q) mx = fmax(mx, fma(sdm[q], o, det[q]));
-            double se = 0.0, sw = 0.0;
+        const int ncol = I * Z;
+        for (int c = tid; c < ncol; c += 2 * ES_THREADS) {
+            const int c2 = c + ES_THREADS;
+            const bool two = c2 < ncol;
+            const double o1 = om[c], o2 = two ? om[c2] : 0.0;     // om[p * Z + bb]
+            double mx1 = -INFINITY, mx2 = -INFINITY;
             for (int q = 0; q < Z; ++q) {
-                const double t = fma(sdm[q], o, det[q]);
-                const double e = exp_neg_fast(mx - t, etab);   // t <= mx; non-finite t makes the sums NaN -> nan_flag
-                se += e;
-                sw = fma(e, t, sw);
+                const double sq = sdm[q], dq = det[q];
+                mx1 = fmax(mx1, fma(sq, o1, dq));
+                mx2 = fmax(mx2, fma(sq, o2, dq));
             }
-            const double lse = mx + log(se);
-            acc += base - (sw / se - lse + logU[bb]);
+            double se1 = 0.0, sw1 = 0.0, se2 = 0.0, sw2 = 0.0;
+            for (int q = 0; q < Z; ++q) {
+                const double sq = sdm[q], dq = det[q];
+                const double t1 = fma(sq, o1, dq), t2 = fma(sq, o2, dq);
+                const double e1 = exp_neg_fast(mx1 - t1, etab);   // t <= mx; non-finite t makes the sums NaN -> nan_flag
+                const double e2 = exp_neg_fast(mx2 - t2, etab);
+                se1 += e1; sw1 = fma(e1, t1, sw1);
+                se2 += e2; sw2 = fma(e2, t2, sw2);
+            }
+            acc += base - (sw1 / se1 - (mx1 + log(se1)) + logU[c % Z]);
+            if (two) acc += base - (sw2 / se2 - (mx2 + log(se2)) + logU[c2 % Z]);
         }
         acc = warp_sum(acc);
         if (lane == 0) red[w] = acc;
