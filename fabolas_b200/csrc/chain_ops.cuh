@@ -102,11 +102,13 @@ __device__ __forceinline__ void inv64_row(double* W, const double* __restrict__ 
 // dinv[8][64]: inverses of the eight 8x8 diagonal blocks of L (row-major).  rinv: 8 x 8 doubles scratch (one
 // set per step).  *failp (shared, zero on entry) receives the 1-based tile-local index of the first
 // non-positive pivot.  W receives L^-1.  Ends with chain_bar().
-__device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv, double* rinv, int* failp, int cw) {
+// nb (1..8): number of 8-row blocks of the tile that hold observations; the blocks beyond (padding of the last tile
+// of a ragged problem: identity on the diagonal, zero elsewhere) are their own factor and inverse and are not worked on.
+__device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv, double* rinv, int* failp, int cw, int nb) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     constexpr int NT128 = 32 * NCW;
     if (cw == 0) {
-        for (int jb = 0; jb < 8; ++jb) {
+        for (int jb = 0; jb < nb; ++jb) {
             const int o = 8 * jb;
             double* rv = rinv + 8 * jb;
             PHBC(60);
@@ -118,7 +120,7 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
             PHEC(60);
             PHBC(61);
             if (jb >= 1) named_bar_sync(4, NT128);          // the workers have applied step jb - 1 to the rest of the tile
-            if (jb < 7) {
+            if (jb + 1 < nb) {
                 if (lane < 8) solve_row8(A, o + 8 + lane, o, rv);
                 __syncwarp();
                 double c0, c1;
@@ -135,7 +137,7 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
             PHEC(61);
         }
     } else {
-        for (int jb = 0; jb < 8; ++jb) {
+        for (int jb = 0; jb < nb; ++jb) {
             const int o = 8 * jb;
             const double* rv = rinv + 8 * jb;
             named_bar_sync(3, NT128);                       // block (jb, jb) factored, row block jb + 1 solved
@@ -157,12 +159,12 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
                 }
             } else {
                 const int row = o + 16 + lane + 32 * (cw - 1);       // rows of the row blocks >= jb + 2
-                if (row < TS) solve_row8(A, row, o, rv);
+                if (row < 8 * nb) solve_row8(A, row, o, rv);
             }
             named_bar_sync(5, NT128 - 32);                  // (workers only) column block jb solved, dinv[jb] written
-            if (jb < 6) {
-                // trailing update: block (ib, kb) -= L(ib, jb) L(kb, jb)^T, jb < kb <= ib, except (jb+1, jb+1)
-                const int m = 7 - jb;
+            if (jb + 2 < nb) {
+                // trailing update: block (ib, kb) -= L(ib, jb) L(kb, jb)^T, jb < kb <= ib < nb, except (jb+1, jb+1)
+                const int m = nb - 1 - jb;
                 const int nblk = m * (m + 1) / 2;
                 for (int q0 = cw; q0 < nblk; q0 += 2 * (NCW - 1)) {      // q0 = 1, 2, 3 first: q = 0 is warp 0's block
                     int ib[2], kb[2];
@@ -187,7 +189,7 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
                     for (int u = 0; u < 2; ++u) if (on[u]) blk_store(c0[u], c1[u], A, ib[u], kb[u]);
                 }
             }
-            if (jb < 7) named_bar_arrive(4, NT128);
+            if (jb + 1 < nb) named_bar_arrive(4, NT128);
             switch (jb) {                                   // row block jb of the inverse, off the critical path
             case 0: inv64_row<0>(W, A, dinv, cw - 1); break;
             case 1: inv64_row<1>(W, A, dinv, cw - 1); break;
@@ -198,6 +200,12 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
             case 6: inv64_row<6>(W, A, dinv, cw - 1); break;
             default: inv64_row<7>(W, A, dinv, cw - 1); break;
             }
+        }
+        // padding rows of the inverse: identity blocks on the diagonal, zero elsewhere (the tile products read whole tiles)
+        for (int q = (cw - 1); q < (8 - nb) * 8; q += NCW - 1) {
+            const int ib = nb + (q >> 3), s = q & 7;
+            const double one = (ib == s && g == 2 * t) ? 1.0 : 0.0, one1 = (ib == s && g == 2 * t + 1) ? 1.0 : 0.0;
+            blk_store(one, one1, W, ib, s);
         }
     }
     chain_bar();

@@ -328,7 +328,8 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             double* A = slots + (size_t)sA * TILE_ELEMS;
             double* W = slots + (size_t)sC * TILE_ELEMS;
             PHBC(57);
-            potrf64_chain(A, W, dinv, rinv, &sync[3], cw);
+            const int rows_here = min(TS, N - TS * K);
+            potrf64_chain(A, W, dinv, rinv, &sync[3], cw, (rows_here + 7) >> 3);
             PHEC(57);
             if (cw == 0 && lane == 0 && sync[3] != 0) {
                 if (first_fail == 0) first_fail = TS * K + sync[3];
