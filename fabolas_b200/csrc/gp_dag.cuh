@@ -56,7 +56,7 @@ struct DagArgs {
 __host__ __device__ inline size_t dag_smem_bytes(int nslot, int d, int resident_np) {
     const size_t coords = resident_np ? (size_t)(d + 4) * resident_np : (size_t)(2 * (d + 1) * TS + 2 * TS);
     return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + EXP_TAB_N + 512 + 128 + 64 + 64 + 64 + 4 * TS) + 8 * coords +
-           8 * MAX_SLOTS + 64;
+           8 * MAX_SLOTS + 64 + 512;       // mbarriers, stream counters, op-record ring (4 x 112 B)
 }
 
 // results of other CTAs of the same launch, read by the last CTA: past L1
@@ -279,6 +279,17 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(
         cbase + (a.resident ? (size_t)(d + 4) * Np : (size_t)(2 * SL + 2 * TS)));
     int* sync = reinterpret_cast<int*>(bars + MAX_SLOTS);     // [0] bulk warp arrivals, [1] chain ops done, [2] failure, [3] per-tile failure
+    // ring of the next bulk op records (28 ints each), filled by cp.async three ops ahead by lanes 0..6 of warp 0:
+    // no thread ever waits for an op record or a load list in global memory
+    int* ring = sync + 16;
+    const bool ring_lane = w == 0 && lane < 7;
+    auto ring_fetch = [&](int opi) {          // every call commits exactly one group (empty past the end)
+        if (ring_lane) {
+            if (opi < a.nbulk) cp_async16(ring + (opi & 3) * 28 + 4 * lane, reinterpret_cast<const int4*>(a.bulk + opi) + lane);
+            cp_async_commit();
+        }
+    };
+    ring_fetch(0); ring_fetch(1); ring_fetch(2);
 
     const Hyper hfull = decode_hyper(gd, a.theta + (size_t)b * Pk, a.yerr2[b]);
     Hyper h;                              // scalars only: hfull.scale[] is indexed dynamically and lives in local memory
@@ -306,6 +317,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             for (int s = 0; s < MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
         sync[0] = 0; sync[1] = 0; sync[2] = 0; sync[3] = 0;
     }
+    if (ring_lane) cp_async_wait<2>();    // op record 0 has landed; the barrier publishes it
     __syncthreads();                      // the only block-wide barrier of an evaluation: the two streams part here
 
     if (w >= NWARPS) {
@@ -398,22 +410,17 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     int cur_r = -1, cur_c = -1;           // tile rows whose coordinate slices are staged (slice mode)
 
     PHB(40);
-    // the head of the next op record (12 ints, L2 latency) is fetched while the current op executes
-    const int4* nxp = reinterpret_cast<const int4*>(a.bulk);
-    int4 n0 = __ldg(nxp), n1 = __ldg(nxp + 1), n2 = __ldg(nxp + 2);
     for (int i = 0; i < a.nbulk; ++i) {
         PHB(41);
         TRB(i, 0);
-        const DagOp* op = a.bulk + i;
-        const int type = n0.x, I = n0.y, J = n0.z, k = n0.w;
-        const int sA = n1.x, sB = n1.y, sC = n1.z;
-        const int wo = n1.w, wait_mask = n2.x, flags = n2.y, st_slot = n2.z, st_tile = n2.w;
+        const int* rec = ring + (i & 3) * 28;         // published by the previous barrier
+        const int type = rec[0], I = rec[1], J = rec[2], k = rec[3];
+        const int sA = rec[4], sB = rec[5], sC = rec[6];
+        const int wo = rec[7], wait_mask = rec[8], flags = rec[9], st_slot = rec[10], st_tile = rec[11];
         if (tid == 0 && (flags & DOPF_WAIT_READ)) bulk_s2g_wait_read();
+        if (ring_lane) cp_async_wait<1>();            // record i + 1 has landed (i + 2 may still be in flight)
         named_bar_sync(1, DAG_BULK_THREADS);          // every bulk warp is done with the previous operation
-        if (i + 1 < a.nbulk) {
-            nxp = reinterpret_cast<const int4*>(a.bulk + i + 1);
-            n0 = __ldg(nxp); n1 = __ldg(nxp + 1); n2 = __ldg(nxp + 2);
-        }
+        ring_fetch(i + 3);                            // into the slot of record i - 1
         if (wo > 0) {
             // chain op c publishes two events: 2c + 1 (tiles final) and 2c + 2 (vectors); a panel solve that only
             // waits for its own diagonal tile starts on the first and takes z before its epilogue
@@ -422,11 +429,11 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             __syncwarp();
         }
         if (tid == 0) {
-            const int nload = __ldg(&op->nload);
+            const int nload = rec[12];
             if (flags & DOPF_DRAIN) bulk_s2g_wait_all();
             if (nload > 0) fence_proxy_async();
             for (int l = 0; l < nload; ++l) {
-                const int ls = __ldg(&op->ld_slot[l]), lt = __ldg(&op->ld_tile[l]);
+                const int ls = rec[13 + l], lt = rec[19 + l];
                 bulk_g2s(slots + (size_t)ls * TILE_ELEMS, ws_tile(lt), TILE_BYTES, &bars[ls]);
             }
             if (st_slot >= 0)

@@ -117,6 +117,27 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #endif
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, completion by commit / wait groups of
+// the issuing thread.  Used for the op-record ring of the fused GP kernel.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+#ifdef FAB_CUSIM
+    memcpy(dst_smem, src_gmem, 16);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef FAB_CUSIM
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef FAB_CUSIM
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // Every thread that wrote (with ordinary stores) shared memory that a bulk store is about to read
 // calls this BEFORE the block barrier that precedes bulk_s2g (generic -> async proxy ordering).
 __device__ __forceinline__ void fence_proxy_async() {
