@@ -443,7 +443,13 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
                     // free or dead slots first, the one idle for longest first (its reload can be hoisted furthest)
                     if (S[q].id < 0) score = (1LL << 40) - S[q].lastB;
                     else if (nu == (1 << 30) && !awaiting_store) score = (1LL << 36) - S[q].lastB;   // dead
-                    else if (S[q].clean) score = nu;
+                    else if (S[q].clean) {
+                        // farthest next use -- except that a slot the bulk stream has only just finished with cannot be
+                        // refilled ahead of time (its reload would be issued and awaited in the same op): last resort.
+                        // Costs a few more reloads, removes most of the waits for them (N = 2048: -15 %).
+                        score = nu;
+                        if (o.stream == 0 && S[q].lastB >= o.idx - 1) score = 2 + (score >> 6);
+                    }
                     else continue;                                   // live and not in the workspace: pinned
                     if (for_chain && S[q].storeB >= 0) {
                         // the chain can only take a slot whose bulk store is known to have been read out
