@@ -50,7 +50,10 @@ enum DagOpFlags {
     DOPF_PUT_BARRIER = 128 // slot C is an operand slot of this very op (no other slot was free): the bulk warps meet first
 };
 constexpr int DAG_MAX_LOADS = 6;
-constexpr int DAG_PREFETCH_DEPTH = 3;
+// A reload is issued at most this many ops ahead of its consumer.  Measured (N = 256, ll+grad): 1 -> 267 us, 2 -> 270,
+// 3 -> 272, 4 -> 275, 6 -> 280: one op (~2 us) covers the L2 / HBM latency of a tile, and a reload hoisted further
+// drags the cross-stream waits of its slot to an earlier op.  N = 2048 does not care (slot availability decides).
+constexpr int DAG_PREFETCH_DEPTH = 1;
 
 struct DagOp {             // 28 ints, read by every thread of its stream
     int type, I, J, k;
