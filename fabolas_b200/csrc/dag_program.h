@@ -5,7 +5,7 @@
 // 64x64 tile tasks.  The kernel runs it on two concurrent instruction streams inside one CTA:
 //   * the BULK stream (8 warps): throughput work -- Matern tile generation, DMMA tile products,
 //     panel solves in GEMM form, the dK contraction;
-//   * the CHAIN stream (1 warp): the latency-bound serial work -- the in-tile Cholesky of each
+//   * the CHAIN stream (4 warps): the latency-bound serial work -- the in-tile Cholesky of each
 //     diagonal tile, its triangular inverse, the forward-substitution vectors.
 // This file decides everything ahead of time, once per (NT, slots, mode): the order of the tasks on
 // each stream (list scheduling on estimated costs, critical path first), the shared-memory slot of

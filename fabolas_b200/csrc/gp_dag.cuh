@@ -5,8 +5,8 @@
 // (fabolas.py:62-66, entropy_search.py:73-77), the solver state GP.predict needs (fabolas.py:187) and
 // grad_log_likelihood.  The CTA is warp-specialised: eight BULK warps execute the
 // throughput stream (Matern tile generation straight into DMMA accumulator registers, 64^3 DMMA tile
-// products, panel solves in GEMM form against the inverted diagonal tile, the dK contraction) and one
-// CHAIN warp executes the latency-bound stream (in-tile Cholesky and triangular inverse of each diagonal
+// products, panel solves in GEMM form against the inverted diagonal tile, the dK contraction) and four
+// CHAIN warps execute the latency-bound stream (in-tile Cholesky and triangular inverse of each diagonal
 // tile, forward-substitution vectors, log-determinant).  Both interpret the static program built on the
 // host (dag_program.h): slots, TMA prefetches, write-through stores and cross-stream waits are all
 // precomputed; the streams meet only through two shared-memory completion counters (release/acquire).
