@@ -339,6 +339,15 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             TRC(j, 1);
             double* A = slots + (size_t)sA * TILE_ELEMS;
             double* W = slots + (size_t)sC * TILE_ELEMS;
+            // the observations of this tile row are fetched now (L2 latency) and used after the factorisation
+            double yv[2] = {0.0, 0.0};
+            if (cw == 0) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int gi = TS * K + lane + 32 * half;
+                    if (gi < N) yv[half] = __ldg(&gd.y[gi]) - gd.mean;
+                }
+            }
             PHBC(57);
             const int rows_here = min(TS, N - TS * K);
             potrf64_chain(A, W, dinv, rinv, &sync[3], cw, (rows_here + 7) >> 3);
@@ -358,13 +367,13 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int r = lane + 32 * half, gi = TS * K + r;
-                    crhs[r] = (gi < N) ? (__ldg(&gd.y[gi]) - gd.mean) - accw[gi] : 0.0;
+                    crhs[r] = (gi < N) ? yv[half] - accw[gi] : 0.0;
                 }
             }
             chain_bar();
             zz += tile_matvec_rows(W, crhs, zv + TS * K, cz, cw);
-            chain_bar();
             if (a.mode >= DAG_FIT) {      // alpha_K starts as W_KK^T z_K; the bulk stream adds W_IK^T z_I, I > K
+                chain_bar();
                 double a0, a1;
                 tile_matvec_t_rows(W, cz, a0, a1, cw);
                 cpart[cw * TS + lane] = a0; cpart[cw * TS + lane + 32] = a1;
