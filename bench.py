@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 METRIC = "GP loglik+grad evals/sec (N=256, 128 walkers/GPU)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one gp_dag_kernel launch from the committed ncu --set full
 # capture (profiles/); None until a capture of the current kernel exists.
-TRAFFIC_BYTES_PER_LAUNCH = 178688 + 1561856
-TRAFFIC_SOURCE = ("profiles/r01ai_ncu_full_raw.csv: dram__bytes_read.sum 179 KB + dram__bytes_write.sum 1.56 MB per "
+TRAFFIC_BYTES_PER_LAUNCH = 186880 + 1583360
+TRAFFIC_SOURCE = ("profiles/r01aj_ncu_full_raw.csv: dram__bytes_read.sum 187 KB + dram__bytes_write.sum 1.58 MB per "
                   "launch of 128 evals (algorithmic bytes 128 x 14.4 KB = 1.84 MB; tiles stream through L2 only)")
 UNIT = "evals/s"
 CONFIG_ID = 2
