@@ -49,11 +49,13 @@ __device__ __forceinline__ WarpTile warp_tile() {
     wt.n0 = ((w >> 2) ? 3 - (w & 3) : (w & 3)) * 16;
     return wt;
 }
-// 8 warps as 4 x 2 blocks of 16 x 16 over a 64 x 32 output
+// 8 warps as 4 x 2 blocks of 16 x 16 over a 64 x 32 output.  Warps w and w + 4 share an SM sub-partition: the upper
+// four warps take the row blocks in reverse order, so that the two row blocks of a sub-partition are r and 3 - r and a
+// product whose k-range grows with the row (lower-triangular left operand) loads every sub-partition alike.
 __device__ __forceinline__ WarpTile warp_tile_32() {
     const int w = threadIdx.x >> 5;
     WarpTile wt;
-    wt.m0 = (w >> 1) * 16;
+    wt.m0 = ((w < 4) ? (w >> 1) : 3 - ((w - 4) >> 1)) * 16;
     wt.n0 = (w & 1) * 16;
     return wt;
 }
