@@ -92,9 +92,11 @@ def _model_theta(hypers, ndim):
         return np.column_stack([np.log(h[:, 0] / ndim), h[:, 1:-3], h[:, -3:-1]]), h[:, -1]
 
 
-def get_candidate(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_innovations=20, batched_fd=False,
-                  burn_in=100, iterations=500, maxiter=None):
-    """fabolas.py:120-264."""
+def prepare_candidate_search(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_innovations=20, burn_in=100,
+                             iterations=500):
+    """fabolas.py:120-254, everything before the optimiser: hyper-posterior samples of the function and the cost
+    model, the resident model batches, representers, EI, p_min, innovations.  Returns (models, cost_models,
+    starting_point); `models` carries the Entropy-Search state (prepare_entropy_search)."""
     if len(dataset["size"].shape) == 1:
         dataset["size"] = dataset["size"].reshape(-1, 1)
     X = np.concatenate([dataset["X"], dataset["size"]], axis=1)
@@ -130,18 +132,32 @@ def get_candidate(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_innov
 
     ctheta, cnoise = _model_theta(cost_hypers, D)
     cost_models = ModelBatch(FAB_FAMILY_M52_BASIS, X, dataset["c"], ctheta, cnoise, amp_mult=D)
-
-    logging.info("Ready to optimize Information Gain by Cost")
     imax = np.argmax(dataset["y"])
     starting_point = np.concatenate([dataset["X"][imax], dataset["size"][imax]])
+    return models, cost_models, starting_point
+
+
+def batched_fd_objective(cost_models, models, h=1e-8):
+    """value and forward-difference gradient of -information_gain_cost from ONE batched
+    call (x and the D points x + h e_k), the numbers L-BFGS-B otherwise collects with D + 1 separate objective calls
+    (scipy's default `2-point` scheme with the same absolute step)."""
+    def fun(x):
+        pts = np.vstack([x] + [x + h * e for e in np.eye(len(x))])
+        v = -information_gain_cost_batch(pts, cost_models, models)
+        return v[0], (v[1:] - v[0]) / h
+    return fun
+
+
+def get_candidate(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_innovations=20, batched_fd=False,
+                  burn_in=100, iterations=500, maxiter=None):
+    """fabolas.py:120-264."""
+    models, cost_models, starting_point = prepare_candidate_search(
+        dataset, bounds, n_hyper_samples, n_gen_samples, n_innovations, burn_in, iterations)
+    logging.info("Ready to optimize Information Gain by Cost")
     opts = {} if maxiter is None else {"maxiter": maxiter}
     if batched_fd:
-        # feed L-BFGS-B value and forward-difference gradient from ONE batched call
-        def fun(x, h=1e-8):
-            pts = np.vstack([x] + [x + h * e for e in np.eye(len(x))])
-            v = -information_gain_cost_batch(pts, cost_models, models)
-            return v[0], (v[1:] - v[0]) / h
-        return minimize(fun=fun, x0=starting_point, jac=True, method="L-BFGS-B", bounds=bounds, options=opts)
+        return minimize(fun=batched_fd_objective(cost_models, models), x0=starting_point, jac=True, method="L-BFGS-B",
+                        bounds=bounds, options=opts)
     return minimize(fun=lambda x: -information_gain_cost(x, cost_models, models), x0=starting_point,
                     method="L-BFGS-B", bounds=bounds, options=opts)
 

@@ -105,6 +105,61 @@ def acquisition_cases():
     print("acq_ref.npz: ig", ig, "igc", igc)
 
 
+def acquisition_case_full():
+    """The reference's own sizes (fabolas.py:120: n_gen_samples=50, n_innovations=20) on its own data: the svm_mnist
+    prior (N=100, D=3), B=8 hyper-samples, Z=50, I=20.  p_min (1.5 MB per model) is NOT stored: the CUDA path computes
+    its own joint_min from the same (mu, cov) and is compared with the reference's information gain end to end, with
+    the reference's logP and strided samples of its derivative tensors stored for the EPMGP leg."""
+    import pandas as pd
+    df = pd.read_csv("/root/reference/prior/prior_svm_mnist.csv")
+    Xh = np.column_stack([np.log10(df["C"].to_numpy()), np.log10(df["gamma"].to_numpy())])
+    s = df["size"].to_numpy(dtype=float)
+    y = df["validation_score"].to_numpy(dtype=float)
+    c = np.log10(df["time_s"].to_numpy(dtype=float))
+    c = c - min(c.min(), 0.0)                                        # fabolas.py:270-273 (costs shifted to >= 0)
+    N, d = Xh.shape
+    B, Z, I = 8, 50, 20
+    rng = np.random.default_rng(23)
+    Xraw = np.column_stack([Xh, s])
+    Xtrain = np.column_stack([Xh, (1 - s) ** 2])
+    bounds = [(-10, 10), (-10, 10), (1 / 256, 1)]
+    theta = np.column_stack([rng.uniform(-1, 0.5, B), rng.uniform(1, 4, (B, d)), rng.uniform(-1, 1, B),
+                             rng.uniform(-1, 1, B)])
+    yerr2 = rng.uniform(1e-3, 1e-2, B)
+    ctheta = theta + 0.1
+    models, cost_models, reps, pmin, U, Omega, mus, covs = [], [], [], [], [], [], [], []
+    for b in range(B):
+        m = go.GP(go.build_kernel(1, theta[b], d + 1), mean=y.mean()); m.compute(Xtrain, np.sqrt(yerr2[b]))
+        cm = go.GP(go.build_kernel(1, ctheta[b], d + 1), mean=c.mean()); cm.compute(Xraw, np.sqrt(yerr2[b]))
+        models.append(m); cost_models.append(cm)
+        R = rng.uniform([lo for lo, _ in bounds], [hi for _, hi in bounds], (Z, d + 1))
+        reps.append(R)
+        mu, cov = m.predict(y, R, return_cov=True)
+        cov = np.clip(cov, np.finfo(cov.dtype).eps, np.inf)         # fabolas.py:192
+        mus.append(mu); covs.append(cov)
+        ei = ref_acq.expected_improvement(mu, cov, m.sample(R, rng=rng))
+        U.append(np.clip(ei, np.finfo(ei.dtype).eps, np.inf))       # fabolas.py:201-205
+        pmin.append(ref_epmgp.joint_min(mu, cov, with_derivatives=True))
+        Omega.append([rng.normal(size=Z).reshape(-1, 1) for _ in range(I)])
+        print("  model", b, "joint_min done", flush=True)
+    dataset = {"y": y, "c": c}
+    tests = rng.uniform([lo for lo, _ in bounds], [hi for _, hi in bounds], (8, d + 1))
+    tests[0] = Xraw[np.argmax(y)]                                    # the optimiser's starting point (fabolas.py:252-254)
+    ig = np.array([ref_acq.information_gain(t, models, pmin, reps, U, Omega, dataset, n_innovations=I, enable_log=False)
+                   for t in tests])
+    igc = np.array([ref_acq.information_gain_cost(t, cost_models, models, dataset, pmin, reps, U, Omega, n_innovations=I)
+                    for t in tests])
+    pm = np.array([ref_acq.predict_testpoint_george(models, y, t) for t in tests])
+    np.savez_compressed(
+        os.path.join(HERE, "acq_ref_full.npz"), Xraw=Xraw, Xtrain=Xtrain, y=y, c=c, theta=theta, ctheta=ctheta,
+        yerr2=yerr2, reps=np.array(reps), U=np.array(U), Omega=np.array(Omega)[..., 0], tests=tests,
+        mu_reps=np.array(mus), cov_reps_clipped=np.array(covs),
+        pmin_logP=np.array([p[0] for p in pmin]), pmin_dMu=np.array([p[1] for p in pmin]),
+        pmin_dSg_s7=np.array([p[2][::7, ::7] for p in pmin]), pmin_dMM_s7=np.array([p[3][::7, ::7, ::7] for p in pmin]),
+        ig=ig, igc=igc, pred_model=pm)
+    print("acq_ref_full.npz: ig", ig, "igc", igc)
+
+
 def prior_cases():
     xs = np.concatenate([np.linspace(-0.5, 4.5, 41), [1e-8, 1e-3, 3.85, 3.87]])
     hs = np.array([Horseshoe(scale=0.1).logpdf(x) for x in xs])
@@ -158,8 +213,12 @@ def gp_cases():
 
 
 if __name__ == "__main__":
+    if "--full-only" in sys.argv:          # the ~2 min full-size information-gain case alone
+        acquisition_case_full()
+        sys.exit(0)
     epmgp_cases()
     acquisition_cases()
+    acquisition_case_full()
     prior_cases()
     ard_cases()
     gp_cases()

@@ -148,6 +148,35 @@ def test_large_history_loglik_gpu(gpu_engine, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [1000, 2048])
+def test_large_history_gradient_gpu(gpu_engine, N):
+    """Gradient parity where the tiles no longer fit the shared-memory slots (NT = 16 / 32 tile rows cycling through
+    six slots; W = L^-1 and the dK contraction read spilled tiles back through TMA): two walkers against the oracle."""
+    if N == 2048:
+        w = gp_workload(5, n_walkers=2)
+        _check(gpu_engine, w["X"], w["y"], w["theta"], w["yerr2"], w["family"], grad=True, amp_mult=w["amp_mult"])
+    else:
+        X, y, theta, yerr2 = _problem(N, 6, 1, 2, seed=N)
+        _check(gpu_engine, X, y, theta, yerr2, 1, grad=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nslot,slices", [(4, False), (5, False), (4, True)])
+def test_tile_streaming_path_n512_gpu(gpu_engine, nslot, slices):
+    """N = 512 (36 tiles) squeezed through 4 / 5 slots, and with the coordinate slices staged per tile (the large-N
+    mode of the covariance generation and the contraction): every tile is evicted and reloaded several times."""
+    X, y, theta, yerr2 = _problem(512, 6, 1, 3, seed=77)
+    try:
+        gpu_engine.debug_set_max_slots(nslot)
+        gpu_engine.debug_force_slices(slices)
+        _check(gpu_engine, X, y, theta, yerr2, 1, grad=True)
+        _check(gpu_engine, X, y, theta, yerr2, 1, grad=False)
+    finally:
+        gpu_engine.debug_set_max_slots(6)
+        gpu_engine.debug_force_slices(False)
+
+
+@pytest.mark.gpu
 def test_golden_svm_mnist_prior_gpu(gpu_engine):
     g = golden("gp_oracle_svm_mnist.npz")                      # the reference's real prior CSV (N=100, D=3)
     gpu_engine.set_data(1, g["X"], g["y"], float(g["y"].mean()), 3)

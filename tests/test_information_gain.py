@@ -91,3 +91,57 @@ def test_information_gain_full_pipeline_vs_oracle_gpu(gpu_engine):
     for x in (0, 7, 23):
         ref = ao.information_gain(cand[x], models, pmin, list(reps), Ul, Om, {"y": w["y"]}, n_innovations=I)
         assert abs(float(ig[x]) - ref) < 1e-6 * max(1.0, abs(ref))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Full-size case from the REFERENCE's own code (tests/golden/make_golden.py: acquisition_case_full): its real svm_mnist
+# prior (N=100, D=3), B=8 hyper-samples, Z=50 representers, I=20 innovations -- the sizes fabolas.get_candidate uses.
+# The whole CUDA pipeline (fit -> predict at representers -> clip -> EPMGP -> es_setup -> information gain) against
+# the reference's information_gain / information_gain_cost values; p_min against the reference's epmgp.joint_min
+# (north star: P_min within 1e-6 absolute).
+# ---------------------------------------------------------------------------------------------------
+def _full_pipeline(eng, cost_engine_factory):
+    import torch
+    g = golden("acq_ref_full.npz")
+    D = g["Xtrain"].shape[1]
+    eng.set_data(1, g["Xtrain"], g["y"], float(g["y"].mean()), D)
+    eng.fit(g["theta"], g["yerr2"])
+    mu, var, cov = eng.predict(g["reps"], want_cov=True)
+    eps = np.finfo(np.float64).eps
+    cov_clip = torch.clamp(cov, min=eps)                                           # fabolas.py:192
+    assert np.max(np.abs(mu.cpu().numpy() - g["mu_reps"])) < 1e-9 * max(1.0, np.abs(g["mu_reps"]).max())
+    scale = np.abs(np.diagonal(g["cov_reps_clipped"], axis1=1, axis2=2)).max()
+    assert np.max(np.abs(cov_clip.cpu().numpy() - g["cov_reps_clipped"])) < 1e-9 * scale
+    logP, dMu, dSg, dMM, info = eng.joint_min(mu, cov_clip)
+    assert int(info.cpu().numpy().max()) == 0
+    assert np.max(np.abs(np.exp(logP.cpu().numpy()) - np.exp(g["pmin_logP"]))) < 1e-6
+    assert np.allclose(dMu.cpu().numpy(), g["pmin_dMu"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(dSg.cpu().numpy()[:, ::7, ::7], g["pmin_dSg_s7"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(dMM.cpu().numpy()[:, ::7, ::7, ::7], g["pmin_dMM_s7"], rtol=1e-5, atol=1e-6)
+    eng.es_setup(g["reps"], cov, (logP, dMu, dSg, dMM), g["U"], g["Omega"])
+    ig, flag, mm, mv = eng.information_gain(g["tests"], return_mixture=True)
+    ig = ig.cpu().numpy()
+    assert int(flag.cpu().numpy().max()) == 0
+    assert np.max(np.abs(ig - g["ig"]) / np.abs(g["ig"])) < 1e-6, (ig, g["ig"])
+    assert np.allclose(mm.cpu().numpy(), g["pred_model"][:, 0], rtol=1e-9, atol=1e-12)
+    assert np.allclose(mv.cpu().numpy(), g["pred_model"][:, 1], rtol=1e-8, atol=1e-12)
+    cost = cost_engine_factory()
+    cost.set_data(1, g["Xraw"], g["c"], float(g["c"].mean()), D)
+    cost.fit(g["ctheta"], g["yerr2"])
+    cmu, = cost.predict(g["tests"], want_var=False)
+    igc = ig / (cmu.cpu().numpy().mean(0) + 1e-4)                                  # acquisitions.py:170-183
+    assert np.max(np.abs(igc - g["igc"]) / np.abs(g["igc"])) < 1e-6
+    cost.close()
+
+
+@pytest.mark.gpu
+def test_information_gain_full_size_matches_reference_gpu(gpu_engine):
+    from fabolas_b200 import Engine
+    _full_pipeline(gpu_engine, lambda: Engine("cuda:0"))
+
+
+def test_information_gain_full_size_matches_reference_emulated(sim_engine):
+    """The same full-size case through the kernel emulator (CPU tier: kernel logic against the reference's numbers)."""
+    from tests.cusim.build_sim import build_sim
+    from fabolas_b200 import Engine
+    _full_pipeline(sim_engine, lambda: Engine(device="cpu", lib_path=build_sim()))

@@ -220,16 +220,54 @@ def test_ard_epmgp_horseshoe_gpu(gpu_runtime):
     _ard_and_epmgp_and_horseshoe(gpu_runtime)
 
 
+def _svm_mnist_dataset():
+    g = golden("gp_oracle_svm_mnist.npz")                       # the reference's svm_mnist prior (CSV is not on the GPU box)
+    X = g["X"][:, :2]; s = 1 - np.sqrt(g["X"][:, 2])
+    return {"X": X.copy(), "y": g["y"].copy(), "size": s.copy(), "c": np.log10(1 + 100 * s) + 0.5}
+
+
+def _batched_fd_equals_plain(ds, bounds, **kw):
+    """the batched objective (value + forward differences from ONE information-gain call) must
+    feed L-BFGS-B the same numbers as the reference's per-point calls (fabolas.py:257-264: scipy's 2-point scheme,
+    absolute step 1e-8), and the optimiser must then walk the same path."""
+    from scipy.optimize import approx_fprime, minimize
+    from fabolas_b200 import fabolas as ff
+    from fabolas_b200.acquisitions import information_gain_cost
+    np.random.seed(1)
+    models, cost_models, x0 = ff.prepare_candidate_search(ds, bounds, **kw)
+    plain = lambda x: -information_gain_cost(x, cost_models, models)
+    fun = ff.batched_fd_objective(cost_models, models)
+    rng = np.random.default_rng(0)
+    pts = [x0] + [np.array([rng.uniform(lo + 0.05 * (hi - lo), hi - 0.05 * (hi - lo)) for lo, hi in bounds]) for _ in range(3)]
+    for x in pts:
+        v, g = fun(x)
+        assert v == plain(x)                                     # same kernels, same inputs: bit-identical value
+        gref = approx_fprime(x, plain, 1e-8)
+        assert np.allclose(g, gref, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(gref).max())), (g, gref)
+    ra = minimize(fun=fun, x0=x0, jac=True, method="L-BFGS-B", bounds=bounds, options={"maxiter": 4})
+    rb = minimize(fun=plain, x0=x0, method="L-BFGS-B", bounds=bounds, options={"maxiter": 4})
+    span = np.array([hi - lo for lo, hi in bounds])
+    assert abs(ra.fun - rb.fun) <= 1e-3 * max(1.0, abs(rb.fun)), (ra.fun, rb.fun)
+    assert np.all(np.abs(ra.x - rb.x) <= 1e-2 * span), (ra.x, rb.x)
+    assert all(lo <= v <= hi for v, (lo, hi) in zip(ra.x, bounds)) and np.isfinite(ra.fun)
+    return ra
+
+
+def test_batched_fd_equals_plain_emulated(sim_runtime):
+    X, s, y, c = _toy(12)
+    ds = {"X": X.copy(), "y": y.copy(), "size": s.copy(), "c": c.copy()}
+    _batched_fd_equals_plain(ds, [(-1, 1), (-1, 1), (1 / 256, 1)], n_hyper_samples=4, n_gen_samples=6, n_innovations=3,
+                             burn_in=2, iterations=3)
+
+
 @pytest.mark.gpu
 def test_fabolas_get_candidate_gpu(gpu_runtime):
-    """One full FABOLAS candidate search on the reference's svm_mnist prior (N=100, D=3), with the
-    reference's K=20 / Z=50 / I=20 and a shortened chain."""
-    import pandas as pd  # noqa: F401  (same loader logic as svm_mnist.load_prior; CSV is not on the GPU box)
+    """One FABOLAS candidate search on the reference's svm_mnist prior (N=100, D=3) with the reference's K=20 / Z=50 /
+    I=20 and a shortened chain: batched-FD objective == plain path (values bit-identical, gradients and the L-BFGS-B
+    result agree), then get_candidate itself end to end."""
     from fabolas_b200 import fabolas as ff
-    np.random.seed(1)
-    g = golden("gp_oracle_svm_mnist.npz")
-    X = g["X"][:, :2]; s = 1 - np.sqrt(g["X"][:, 2])
-    ds = {"X": X.copy(), "y": g["y"].copy(), "size": s.copy(), "c": np.log10(1 + 100 * s) + 0.5}
     bounds = [(-10, 10), (-10, 10), (1 / 256, 1)]
-    r = ff.get_candidate(ds, bounds, burn_in=20, iterations=40, maxiter=5, batched_fd=True)
+    _batched_fd_equals_plain(_svm_mnist_dataset(), bounds, burn_in=20, iterations=40)
+    np.random.seed(1)
+    r = ff.get_candidate(_svm_mnist_dataset(), bounds, burn_in=20, iterations=40, maxiter=5, batched_fd=True)
     assert r.x.shape == (3,) and np.isfinite(r.fun) and all(lo <= v <= hi for v, (lo, hi) in zip(r.x, bounds))
