@@ -139,7 +139,8 @@ void mpeer_release(fab_ctx* c) {
     if (c->mpeer.world > 0 && c->mpeer.base[c->mpeer.rank]) cudaFree(c->mpeer.base[c->mpeer.rank]);
     c->mpeer = fab_ctx::McPeer();
 }
-inline size_t peer_ctrl_offset(const fab_ctx::Peer& p) { return 2 * p.buf_bytes; }     // +0 arrivals, +64 local CTAs done, +128 error flag
+constexpr size_t ES_ENTROPY_SMEM_OPTIN = 100 * 1024;
+inline size_t peer_ctrl_offset(const fab_ctx::Peer& p) { return 2 * p.buf_bytes; }     // +0 arrival slots (one u32 per source rank), +64 local CTAs done, +128 error flag
 
 }  // namespace
 
@@ -162,7 +163,7 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
     cudaFuncSetAttribute(gp_predict_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(epmgp_ep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(epmgp_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(es_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(es_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ES_ENTROPY_SMEM_OPTIN);
     cudaFuncSetAttribute(gp_predict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(mcmc_stretch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - MCMC_STATIC_SMEM);
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->num_sms = v;
@@ -289,8 +290,11 @@ static int dag_setup(fab_ctx* c, int B, int mode, size_t smem_limit, DagArgs* ou
         if (!dv.host.ok) return fail(c, FAB_EUNSUPPORTED, dv.host.err.c_str());
         dv.nbulk = (int)dv.host.bulk.size(); dv.nchain = (int)dv.host.chain.size();
         if (cudaMalloc(reinterpret_cast<void**>(&dv.bulk), (dv.nbulk + 1) * sizeof(DagOp)) != cudaSuccess ||
-            cudaMalloc(reinterpret_cast<void**>(&dv.chain), (dv.nchain + 1) * sizeof(DagOp)) != cudaSuccess)
+            cudaMalloc(reinterpret_cast<void**>(&dv.chain), (dv.nchain + 1) * sizeof(DagOp)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(dv.bulk);                        // null when the first allocation is the one that failed
             return fail(c, FAB_ENOMEM, "tile program allocation failed");
+        }
         it = c->dag.emplace(key, std::move(dv)).first;          // host vectors stay alive: async copy sources
         FAB_CUDA(c, cudaMemcpyAsync(it->second.bulk, it->second.host.bulk.data(), it->second.nbulk * sizeof(DagOp),
                                     cudaMemcpyHostToDevice, c->stream));
@@ -332,10 +336,12 @@ static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int 
         const size_t parity = (size_t)(p.steps & 1ull) * p.buf_bytes;
         for (int r = 0; r < p.world; ++r) {
             a.peer.buf[r] = reinterpret_cast<double*>(static_cast<char*>(p.base[r]) + parity);
-            a.peer.cnt[r] = reinterpret_cast<unsigned*>(static_cast<char*>(p.base[r]) + peer_ctrl_offset(p));
+            a.peer.slots[r] = reinterpret_cast<unsigned*>(static_cast<char*>(p.base[r]) + peer_ctrl_offset(p));
         }
         a.peer.done = reinterpret_cast<unsigned*>(static_cast<char*>(p.base[p.rank]) + peer_ctrl_offset(p) + 64);
+        a.peer.err = reinterpret_cast<int*>(static_cast<char*>(p.base[p.rank]) + peer_ctrl_offset(p) + 128);
         a.peer.done_target = (unsigned)((p.steps + 1) * (unsigned long long)B);
+        a.peer.step = (unsigned)(p.steps + 1);
         a.peer.world = p.world; a.peer.rank = p.rank; a.peer.rows_per_rank = p.rows_per_rank; a.peer.row_doubles = p.row_doubles;
     }
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
@@ -449,6 +455,8 @@ int fab_es_setup(fab_ctx* c, const double* reps, int Z, const double* cov_reps, 
     if (!c->resident) return fail(c, FAB_ESTATE, "fab_gp_fit_batch has not been called");
     if (!reps || !cov_reps || !logP || !dMu || !dSigma || !dMuMu || !U || !Omega) return fail(c, FAB_EINVAL, "null pointer");
     if (Z < 1 || Z > EP_MAXZ || I < 1) return fail(c, FAB_EUNSUPPORTED, "need 1 <= Z <= 64 representers and I >= 1 innovations");
+    if (es_entropy_smem_bytes(Z, I) > ES_ENTROPY_SMEM_OPTIN)
+        return fail(c, FAB_EUNSUPPORTED, "too many innovations: the innovation vectors of one model (I x Z) must fit the 100 KB of shared memory of the entropy kernel");
     FAB_CUDA(c, cudaSetDevice(c->device));
     const GpData& gd = c->gd;
     const int B = c->wsB;
@@ -625,12 +633,8 @@ int fab_peer_wait(fab_ctx* c, const double** gathered, int* rows, int* row_doubl
     fab_ctx::Peer& p = c->peer;
     if (!p.connected || p.steps == 0) return fail(c, FAB_ESTATE, "no exchanged likelihood step is in flight");
     FAB_CUDA(c, cudaSetDevice(c->device));
+    // nothing to enqueue: the kernel of the step itself returns only when every rank's rows have arrived
     char* base = static_cast<char*>(p.base[p.rank]);
-    unsigned* cnt = reinterpret_cast<unsigned*>(base + peer_ctrl_offset(p));
-    int* err = reinterpret_cast<int*>(base + peer_ctrl_offset(p) + 128);
-    const unsigned expected = (unsigned)(p.steps * (unsigned long long)p.world);      // one signal per rank and step
-    FAB_LAUNCH(peer_wait_kernel, 1, 1, 0, c->stream, cnt, expected, err);
-    FAB_CUDA(c, cudaGetLastError());
     if (gathered) *gathered = reinterpret_cast<const double*>(base + (size_t)((p.steps - 1) & 1ull) * p.buf_bytes);
     if (rows) *rows = p.world * p.rows_per_rank;
     if (row_doubles) *row_doubles = p.row_doubles;

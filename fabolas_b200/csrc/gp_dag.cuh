@@ -22,16 +22,23 @@ constexpr int DAG_BULK_THREADS = NTHREADS;         // warps 0..7
 constexpr int DAG_THREADS = NTHREADS + 32 * NCW;   // + the chain warps
 
 // Peer exchange of the per-walker results (multi-GPU likelihood step): instead of an
-// all-gather after the kernel, the LAST CTA of the launch to finish (local completion counter) pushes this
-// rank's block of result rows [grad (Pk+1) | ll | info] straight into the gather buffer of EVERY rank (NVLink /
-// NVSwitch peer stores by all of its bulk threads; the local rank is just another entry), then one system-scope
-// fence and one arrival signal per rank.  world == 0: no exchange.
+// all-gather after the kernel, every CTA stores its walker's result row [grad (Pk+1) | ll | info] straight into the
+// gather buffer of EVERY rank (plain NVLink / NVSwitch peer stores by a few lanes; the local rank is just another
+// entry) as soon as the walker is done -- the transfers of the early CTAs overlap the evaluations still running.
+// The LAST CTA of the launch to finish (local completion counter, device-scope release/acquire chain from every
+// CTA's stores) issues one system-scope fence, publishes this rank's step number in ITS OWN arrival slot on every
+// rank, and then waits until every rank's slot on THIS rank has reached the step: when the kernel completes, the
+// gather buffer of the step is complete -- one launch per step, no collective, no separate wait kernel.  One slot
+// per source rank (a generation number, not a summed counter): a fast peer's arrival for step s + 1 can never stand
+// in for a missing step-s row.  world == 0: no exchange.
 constexpr int FAB_MAX_PEERS = 8;
 struct PeerTable {
     double* buf[FAB_MAX_PEERS];        // this step's gather buffer of rank r (world x rows_per_rank x row_doubles)
-    unsigned* cnt[FAB_MAX_PEERS];      // arrival counter of rank r (+1 per rank and step)
+    unsigned* slots[FAB_MAX_PEERS];    // arrival slots of rank r: slots[r][src] = last step rank `src` has delivered
     unsigned* done;                    // local: CTAs of this rank that have finished (monotonic over steps)
+    int* err;                          // local: set when a wait gave up (a peer never delivered)
     unsigned done_target;              // value of *done once every CTA of THIS step has finished
+    unsigned step;                     // generation number of this step (1, 2, ...)
     int world, rank, rows_per_rank, row_doubles;
 };
 
@@ -57,22 +64,6 @@ __host__ __device__ inline size_t dag_smem_bytes(int nslot, int d, int resident_
     const size_t coords = resident_np ? (size_t)(d + 4) * resident_np : (size_t)(2 * (d + 1) * TS + 2 * TS);
     return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + EXP_TAB_N + 512 + 128 + 64 + 64 + 64 + 4 * TS) + 8 * coords +
            8 * MAX_SLOTS + 64 + 512;       // mbarriers, stream counters, op-record ring (4 x 112 B)
-}
-
-// results of other CTAs of the same launch, read by the last CTA: past L1
-__device__ __forceinline__ double ld_cg_f64(const double* p) {
-#ifdef FAB_CUSIM
-    return *p;
-#else
-    return __ldcg(p);
-#endif
-}
-__device__ __forceinline__ int ld_cg_i32(const int* p) {
-#ifdef FAB_CUSIM
-    return *p;
-#else
-    return __ldcg(p);
-#endif
 }
 
 // ---- stream synchronisation: completion counters in shared memory ----
@@ -618,63 +609,49 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             go[Pk] = bad ? NAN : 0.5 * gacc[MAX_PK];
         }
     }
-    if (a.peer.world > 0) {
-        // this walker's ll / info (chain) and gradient row (thread 0) are in local memory; count the CTA in
-        named_bar_sync(1, DAG_BULK_THREADS);
-        if (tid == 0) {
-#ifdef FAB_CUSIM
-            const unsigned prev = *a.peer.done; *a.peer.done = prev + 1u;
-#else
-            __threadfence();
-            const unsigned prev = atomicAdd(a.peer.done, 1u);
-            __threadfence();
-#endif
-            sync[4] = (prev + 1u == a.peer.done_target) ? 1 : 0;
+    if (a.peer.world > 0 && w == 0) {
+        // this walker's ll / info (chain, published through sync[1]) and gradient row (lane 0, above) are final:
+        // the first row_doubles lanes of warp 0 store the row into every rank's gather buffer
+        __syncwarp();
+        const int rd = a.peer.row_doubles;
+        if (lane < rd) {
+            double v;
+            if (lane == rd - 2) v = a.ll[b];
+            else if (lane == rd - 1) v = (double)a.info[b];
+            else v = (a.mode == DAG_GRAD && a.grad) ? a.grad[(size_t)b * (Pk + 1) + lane] : 0.0;
+            const size_t off = ((size_t)a.peer.rank * a.peer.rows_per_rank + b) * rd + lane;
+            for (int r = 0; r < a.peer.world; ++r) a.peer.buf[r][off] = v;
         }
-        named_bar_sync(1, DAG_BULK_THREADS);
-        if (sync[4]) {                    // last CTA of this rank: every row of the block is final and visible
-            const int rd = a.peer.row_doubles, nB = a.peer.rows_per_rank;
-            const size_t base = (size_t)a.peer.rank * nB * rd;
-            for (int e = tid; e < nB * rd; e += DAG_BULK_THREADS) {
-                const int bb = e / rd, q = e - bb * rd;
-                double v;
-                if (q == rd - 2) v = ld_cg_f64(&a.ll[bb]);
-                else if (q == rd - 1) v = (double)ld_cg_i32(&a.info[bb]);
-                else v = (a.mode == DAG_GRAD && a.grad) ? ld_cg_f64(&a.grad[(size_t)bb * (Pk + 1) + q]) : 0.0;
-                for (int r = 0; r < a.peer.world; ++r) a.peer.buf[r][base + e] = v;
-            }
-            named_bar_sync(1, DAG_BULK_THREADS);
-            if (tid == 0) {
-#ifndef FAB_CUSIM
-                __threadfence_system();
-                for (int r = 0; r < a.peer.world; ++r)
-                    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(a.peer.cnt[r]) : "memory");
+        __syncwarp();
+        if (lane == 0) {
+#ifdef FAB_CUSIM
+            const unsigned prev = *a.peer.done; *a.peer.done = prev + 1u;      // (the emulator has no peers: world == 1)
+            if (prev + 1u == a.peer.done_target) a.peer.slots[a.peer.rank][a.peer.rank] = a.peer.step;
 #else
-                for (int r = 0; r < a.peer.world; ++r) *a.peer.cnt[r] += 1;
-#endif
+            __threadfence();                          // the row stores of this CTA before its count (release, device scope)
+            const unsigned prev = atomicAdd(a.peer.done, 1u);
+            if (prev + 1u == a.peer.done_target) {    // last CTA of this rank: every row of the block has been stored
+                __threadfence_system();               // acquire the other CTAs' counts, release everything to the box
+                for (int r = 0; r < a.peer.world; ++r)
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.peer.slots[r] + a.peer.rank), "r"(a.peer.step) : "memory");
+                const long long t0 = clock64();
+                for (int r = 0; r < a.peer.world; ++r) {
+                    const unsigned* sl = a.peer.slots[a.peer.rank] + r;
+                    for (;;) {
+                        unsigned v;
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sl) : "memory");
+                        if ((int)(v - a.peer.step) >= 0) break;
+                        if (clock64() - t0 > 4000000000LL) { *a.peer.err = 1; break; }      // ~2 s: a peer died
+                        __nanosleep(40);
+                    }
+                }
             }
+#endif
         }
     }
     if (tid == 0) bulk_s2g_wait_all();
     PHE(51);
     PHE(40);
-}
-
-// Consumer side of the peer exchange: returns when `expected` rows have arrived in this rank's gather buffer
-// (acquire at system scope), or sets *err after ~2 s (a peer died): the launch never hangs the GPU.
-__global__ void peer_wait_kernel(unsigned* cnt, unsigned expected, int* err) {
-#ifndef FAB_CUSIM
-    const long long t0 = clock64();
-    for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-        if ((int)(v - expected) >= 0) break;
-        if (clock64() - t0 > 4000000000LL) { *err = 1; break; }
-        __nanosleep(100);
-    }
-#else
-    if ((int)(*cnt - expected) < 0) *err = 1;
-#endif
 }
 
 // 12 warps: 65536 / 384 = 170 -> 168 registers per thread.

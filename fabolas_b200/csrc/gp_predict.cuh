@@ -294,6 +294,18 @@ __device__ __forceinline__ double ei_value(double mu, double var, double y_max, 
     return sd * (u * cdf + pdf);
 }
 
+// np.argmax ordering of (value, index) pairs: the first occurrence of the maximum wins, and a NaN counts as the
+// maximum (np.argmax returns the index of the first NaN -- expected_improvement.py:92-93 inherits that when a
+// predictive variance is NaN); index < 0 = "no candidate yet".
+__device__ __forceinline__ bool argmax_takes(double ov, long long oi, double best, long long bi) {
+    if (oi < 0) return false;
+    if (bi < 0) return true;
+    const bool on = isnan(ov), bn = isnan(best);
+    if (on != bn) return on;
+    if (on) return oi < bi;
+    return ov > best || (ov == best && oi < bi);
+}
+
 // Grid (G, B): CTA (x, b) scans candidates [x * chunk, (x + 1) * chunk) of model b.  G == 1 writes the result,
 // otherwise the (value, index) pair of the chunk goes to part_val / part_idx [b * G + x] and ei_argmax_final_kernel
 // finishes (np.argmax: the first occurrence of the maximum wins at every level).
@@ -310,19 +322,19 @@ __global__ void __launch_bounds__(NTHREADS) ei_argmax_kernel(EiArgs a, long long
     for (long long c = c0 + tid; c < c1; c += NTHREADS) {
         const double v = ei_value(a.mu[(size_t)b * a.M + c], a.var[(size_t)b * a.M + c], ym, a.xi);
         if (a.ei) a.ei[(size_t)b * a.M + c] = v;
-        if (v > best) { best = v; bi = c; }             // first maximum wins within a thread (ascending c)
+        if (argmax_takes(v, c, best, bi)) { best = v; bi = c; }      // first maximum wins within a thread (ascending c)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
         const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ov; bi = oi; }
+        if (argmax_takes(ov, oi, best, bi)) { best = ov; bi = oi; }
     }
     if (lane == 0) { sval[w] = best; sidx[w] = bi; }
     __syncthreads();
     if (tid == 0) {
         for (int q = 1; q < NWARPS; ++q)
-            if (sval[q] > best || (sval[q] == best && sidx[q] >= 0 && (bi < 0 || sidx[q] < bi))) { best = sval[q]; bi = sidx[q]; }
+            if (argmax_takes(sval[q], sidx[q], best, bi)) { best = sval[q]; bi = sidx[q]; }
         if (gridDim.x == 1) {
             if (a.best_val) a.best_val[b] = best;
             if (a.best_idx) a.best_idx[b] = bi;          // np.argmax: first occurrence of the maximum
@@ -340,13 +352,13 @@ __global__ void ei_argmax_final_kernel(EiArgs a, int G, const double* part_val, 
     for (int x = lane; x < G; x += 32) {                // chunks ascend with x: the first maximum wins
         const double v = part_val[(size_t)b * G + x];
         const long long i = part_idx[(size_t)b * G + x];
-        if (v > best || (v == best && i >= 0 && (bi < 0 || i < bi))) { best = v; bi = i; }
+        if (argmax_takes(v, i, best, bi)) { best = v; bi = i; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
         const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ov; bi = oi; }
+        if (argmax_takes(ov, oi, best, bi)) { best = ov; bi = oi; }
     }
     if (lane == 0) {
         if (a.best_val) a.best_val[b] = best;

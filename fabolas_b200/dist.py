@@ -58,6 +58,13 @@ def sharded_loglik(engine, theta, yerr2, grad: bool = False):
         engine.loglik_exchange(theta[lo:hi], yerr2[lo:hi], grad=grad)
         rows = engine.peer_wait()
         ll, info = rows[:, -2].contiguous(), rows[:, -1].to(torch.int32)
+        # a peer that never delivered leaves stale rows behind: every rank learns about it and raises (the flag is
+        # read after the kernel of the step; the callers of this function consume the rows on the host anyway)
+        bad = torch.tensor([1.0 if engine.peer_error() else 0.0], device=rows.device)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if bad.item() != 0.0:
+            from ._capi import FabolasError
+            raise FabolasError("fused likelihood exchange: a rank did not deliver its rows within the timeout")
         return (ll, rows[:, :-2].contiguous(), info) if grad else (ll, info)
     if hi > lo:
         out = engine.loglik(theta[lo:hi], yerr2[lo:hi], grad=grad)
@@ -73,37 +80,69 @@ def sharded_loglik(engine, theta, yerr2, grad: bool = False):
     return (ll, packed[:, 1:-1].contiguous(), info) if grad else (ll, info)
 
 
-def sharded_argmax(values: torch.Tensor, offset: int):
-    """Global (max value, global index) from per-rank candidate shards: all-gather of one pair per
-    rank, first occurrence wins (np.argmax semantics)."""
+def _argmax_pairs(pairs):
+    """np.argmax over the concatenation, from one (value, global index) pair per shard: a NaN is the maximum, the
+    first occurrence wins, shards without candidates (index < 0) do not take part."""
+    best = None
+    for v, i in pairs:
+        if i < 0:
+            continue
+        if best is None:
+            best = (v, i)
+            continue
+        bv, bi = best
+        if np.isnan(v) != np.isnan(bv):
+            take = bool(np.isnan(v))
+        elif np.isnan(v):
+            take = i < bi
+        else:
+            take = v > bv or (v == bv and i < bi)
+        if take:
+            best = (v, i)
+    if best is None:
+        raise ValueError("argmax of an empty candidate set")
+    return float(best[0]), int(best[1])
+
+
+def sharded_argmax_pair(value: float, index: int, device):
+    """np.argmax over all shards from this rank's (value, GLOBAL index) pair (index < 0: this rank holds no
+    candidates): one all-gather of a pair per rank."""
     rank, size = world()
-    if values.numel():
-        v, i = torch.max(values, dim=0)
-        pair = torch.stack([v.double(), (i + offset).double()])
-    else:
-        pair = torch.tensor([-float("inf"), -1.0], dtype=torch.float64, device=values.device)
     if size == 1:
-        return float(pair[0]), int(pair[1])
-    allp = torch.empty(size * 2, dtype=torch.float64, device=values.device)
+        return _argmax_pairs([(value, index)])
+    pair = torch.tensor([value, float(index)], dtype=torch.float64, device=device)
+    allp = torch.empty(size * 2, dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(allp, pair)
-    allp = allp.view(size, 2).cpu().numpy()
-    best = max(range(size), key=lambda r: (allp[r, 0], -allp[r, 1] if allp[r, 1] >= 0 else -np.inf))
-    return float(allp[best, 0]), int(allp[best, 1])
+    return _argmax_pairs(allp.view(size, 2).cpu().numpy())
+
+
+def sharded_argmax(values: torch.Tensor, offset: int):
+    """Global (max value, global index) of per-rank candidate shards held as tensors (np.argmax semantics: first
+    occurrence, NaN is the maximum)."""
+    if values.numel():
+        nan = torch.isnan(values)
+        if bool(nan.any()):
+            i = torch.nonzero(nan)[0, 0]
+            v = values[i]
+        else:
+            v = values.max()
+            i = torch.nonzero(values == v)[0, 0]            # first occurrence
+        return sharded_argmax_pair(float(v), int(i) + offset, values.device)
+    return sharded_argmax_pair(-float("inf"), -1, values.device)
 
 
 def sharded_ei_argmax(engine, T, y_max, xi: float = 0.0):
-    """expected_improvement.get_candidate's sweep (predict -> EI -> argmax) with the M candidates of T
-    sharded across ranks; the models are resident (replicated) on every rank.  Model 0 decides."""
+    """expected_improvement.get_candidate's sweep (predict -> EI -> argmax, expected_improvement.py:85-93) with the M
+    candidates of T sharded across ranks; the models are resident (replicated) on every rank.  Model 0 decides.  The
+    local argmax is the engine's own (ei_argmax_kernel); only one (value, index) pair per rank is exchanged."""
     rank, size = world()
-    T = np.atleast_2d(np.asarray(T, dtype=np.float64))
+    T = np.atleast_2d(np.asarray(T, dtype=np.float64)) if not isinstance(T, torch.Tensor) else T
     lo, hi = shard_range(T.shape[0], rank, size)
     if hi > lo:
         mu, var = engine.predict(T[lo:hi], want_var=True)
-        ei, _, _ = engine.expected_improvement(mu[:1], var[:1], np.array([y_max]), xi=xi)
-        vals = ei[0]
-    else:
-        vals = engine.empty(0)
-    return sharded_argmax(vals, lo)
+        _, bv, bi = engine.expected_improvement(mu[:1], var[:1], np.array([y_max]), xi=xi, want_ei=False)
+        return sharded_argmax_pair(float(bv[0]), int(bi[0]) + lo, engine.device)
+    return sharded_argmax_pair(-float("inf"), -1, engine.device)
 
 
 def sharded_information_gain(engine, Xc):

@@ -46,6 +46,8 @@ def get_candidate(prior, bounds, n_gen_samples=100, engine=None):
                                   size=(n_gen_samples, X.shape[1]))
     mean, var = engine.predict(X_samples, want_var=True)
     _, _, index = engine.expected_improvement(mean, var, np.array([y.max()]), want_ei=False)
+    if int(index[0]) < 0:
+        raise ArithmeticError("expected improvement has no maximiser over the candidate set")
     return X_samples[int(index[0])]
 
 

@@ -135,6 +135,9 @@ class DeviceEnsembleSampler:
             coords, lp, nacc = self.engine.mcmc_run_sharded(self.prior, coords, nsteps, log_prob=lp, seed=self.seed,
                                                             iter0=self._steps_taken, a=self.a, naccepted=self._nacc)
             chain = chain_lp = None
+            if self.engine.mcmc_peer_error():     # a box-wide barrier gave up: the replicas may have diverged
+                from ._capi import FabolasError
+                raise FabolasError("sharded device sampler: a rank did not reach a half-step barrier within the timeout")
         else:
             coords, lp, chain, chain_lp, nacc = self.engine.mcmc_run(
                 self.prior, coords, nsteps, log_prob=lp, seed=self.seed, iter0=self._steps_taken, a=self.a,

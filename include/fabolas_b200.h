@@ -136,16 +136,21 @@ int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta
  * the GPUs of one box, one process per GPU; the only exchange of the path is the all-gather of the per-walker
  * log-likelihood (+ gradient) after every step -- the reference itself is single-process, fabolas.py:103-117).
  * Instead of a collective after the kernel, the CTA that finishes a walker stores its result row straight into the
- * gather buffer of EVERY rank through NVLink / NVSwitch peer memory and bumps every rank's arrival counter.
- *   fab_peer_alloc    allocates this rank's buffers (two gather buffers by step parity, counter) and writes the
- *                     64-byte CUDA IPC handle to handle_out (host); exchange the handles with any transport
+ * gather buffer of EVERY rank through NVLink / NVSwitch peer memory; the last CTA of a rank publishes the rank's step
+ * number in its own arrival slot on every rank and then waits (inside the same kernel, bounded) until every rank's
+ * slot on this rank has reached the step: ONE launch per step, complete gather buffer when the kernel completes.
+ *   fab_peer_alloc    allocates this rank's buffers (two gather buffers by step parity, one arrival slot per source
+ *                     rank, error flag) and writes the 64-byte CUDA IPC handle to handle_out (host); exchange the
+ *                     handles with any transport
  *   fab_peer_connect  handles: world x 64 bytes (host, rank order); maps the peers' buffers
- *   fab_gp_loglik_exchange  = fab_gp_loglik_batch on this rank's B = rows_per_rank walkers, plus the peer stores
- *   fab_peer_wait     enqueues the wait for all world x B rows of the most recent exchanged step on the stream and
- *                     returns the device pointer of this rank's gathered rows: rows x row_doubles, row of walker b of
- *                     rank r at (r * B + b): [grad (Pk+1; zero when grad was not requested) | ll | info]; valid for
- *                     stream-ordered work until the next-but-one exchanged step
- *   fab_peer_error    synchronises the stream; 1 if a wait gave up after ~2 s (a peer never delivered)          */
+ *   fab_gp_loglik_exchange  = fab_gp_loglik_batch on this rank's B = rows_per_rank walkers, plus the peer stores and
+ *                     the wait for every rank's rows of this step
+ *   fab_peer_wait     enqueues nothing (kept for the call order of the first version of this interface): returns the
+ *                     device pointer of this rank's gathered rows of the most recent exchanged step: rows x
+ *                     row_doubles, row of walker b of rank r at (r * B + b): [grad (Pk+1; zero when grad was not
+ *                     requested) | ll | info]; valid for stream-ordered work until the next-but-one exchanged step
+ *   fab_peer_error    synchronises the stream; 1 if a wait gave up after ~2 s (a peer never delivered): the rows of
+ *                     that step are then stale and the caller must not use them                                  */
 int fab_peer_alloc(fab_ctx* ctx, int rank, int world, int rows_per_rank, void* handle_out);
 int fab_peer_connect(fab_ctx* ctx, const void* handles);
 int fab_gp_loglik_exchange(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll, double* grad,
