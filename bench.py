@@ -1,25 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark: batched GP log-likelihood + gradient evaluations per second.
+"""bench.py -- headline benchmark: batched GP log-likelihood + gradient evaluations per second, and
+Entropy-Search acquisition evaluations per second (the two halves of BASELINE.json's metric).
 
 Workload (BASELINE.json configs[1]): CNN-CIFAR10 search space (5 hyper-parameters) + dataset size s,
 N = 256 synthetic observations, 128 MCMC walkers per GPU, FP64.  A "step" is one batched evaluation
-of ll and d ll / d theta for every walker (weak scaling: 128 walkers on every GPU; the per-walker
-ll vector and gradients are exchanged with an NCCL all-gather when --gpus > 1).
+of ll and d ll / d theta for every walker (weak scaling: 128 walkers on every GPU; at --gpus > 1 every
+rank ends the step holding every walker's [grad | ll | info] row -- the exchange is fused into the kernel).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Prints ONE JSON line (rank 0).  `value` = evaluations/s with inputs resident in HBM; `e2e` = the
-same through the public Python API with HOST (pinned) buffers, host<->device copies inside the timed
-region; `roofline` = the dominant kernel against the measured FP64 peak; `cpu_baseline` = the CPU
-oracle (numpy/scipy restatement of george) timed on this box's host cores.
+Prints ONE JSON line (rank 0).  `value` = evaluations/s with inputs resident in HBM; `e2e` = the same
+through the public Python API with HOST (pinned) buffers, host<->device copies inside the timed region
+(at N > 1: H2D -> exchanged step -> D2H of the GATHERED rows); `roofline` = the dominant kernel against
+the measured FP64 peak; `cpu_baseline` = the CPU oracle (numpy/scipy restatement of george) timed on this
+box's host cores.  `es_acquisition` carries the same four things for the information gain (configs[2]);
+`configs` carries the other BASELINE.json configurations ([0], [3], [4]) and the multi-GPU checks
+(sharded sampler bit-identity, sharded argmax == single-GPU argmax) so that they run under the driver at
+every N.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -29,13 +36,39 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "GP loglik+grad evals/sec (N=256, 128 walkers/GPU)"
-# dram__bytes_read.sum + dram__bytes_write.sum of one gp_dag_kernel launch from the committed ncu --set full
-# capture (profiles/); None until a capture of the current kernel exists.
+UNIT = "evals/s"
+CONFIG_ID = 2
+WALKERS_PER_GPU = 128
+WORKLOAD = ("BASELINE configs[1]: CNN-CIFAR10 space (5 hyper-parameters) + s, N=256, D=6, P=9, 128 walkers per GPU, "
+            "Matern52 x (linear+const) basis kernel, FP64")
+# dram__bytes_read.sum + dram__bytes_write.sum of one gp_dag_kernel launch from the committed ncu --set full capture
 TRAFFIC_BYTES_PER_LAUNCH = 186880 + 1583360
 TRAFFIC_SOURCE = ("profiles/r01aj_ncu_full_raw.csv: dram__bytes_read.sum 187 KB + dram__bytes_write.sum 1.58 MB per "
                   "launch of 128 evals (algorithmic bytes 128 x 14.4 KB = 1.84 MB; tiles stream through L2 only)")
-UNIT = "evals/s"
-CONFIG_ID = 2
+ES_TRAFFIC_BYTES_PER_LAUNCH = None      # es_entropy_kernel; filled from the committed capture (profiles/)
+ES_TRAFFIC_SOURCE = None
+# FP64-pipe instructions of es_entropy_kernel per (candidate, model, innovation, column, row) element -- counted in
+# the source and checked against the SASS of the inner loops
+ES_FP64_INSTR_PER_ELEMENT = 17
+
+
+def bench_config(n_gpus: int) -> dict:
+    """The `config` object BOTH arms print (the driver compares them)."""
+    return {"workload": WORKLOAD, "walkers_per_gpu": WALKERS_PER_GPU, "N": 256, "D": 6, "P": 9,
+            "gpu_arm_l2_flush_between_steps": True,
+            "parallelism": f"walkers sharded x{n_gpus} (one process per GPU); every rank ends a step with every walker's row"}
+
+
+def fp64_peaks():
+    """Measured FP64 peaks of this pool (tools/microbench/fp64_peaks.cu): no silent fallback."""
+    path = os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")
+    if not os.path.exists(path):
+        raise SystemExit(f"{path} is missing: the roofline denominator is a measured number, re-run tools/microbench/fp64_peaks")
+    with open(path) as f:
+        pk = json.load(f)
+    dmma = max(v for k, v in pk.items() if k.startswith("dmma_m8n8k4"))
+    dfma = max(v for k, v in pk.items() if k.startswith("dfma") and isinstance(v, (int, float)))
+    return dmma, dfma
 
 
 # ------------------------------------------------------------------------------------------------
@@ -76,6 +109,34 @@ def cpu_oracle_rate(per_core: int, cores: int | None = None, pool=None):
     return n / dt, cores, n, dt
 
 
+def _es_cpu_worker(args):
+    """acquisitions.information_gain (oracle port, acq_oracle.py) on this worker's candidates; the prepared lists
+    (models' hyper-parameters, representers, p_min, U, Omega) come from files written by the GPU leg."""
+    path, idx = args
+    from threadpoolctl import threadpool_limits
+    from oracle import acq_oracle as ao
+    from oracle import george_oracle as go
+    s = np.load(os.path.join(path, "small.npz"))
+    dSg = np.load(os.path.join(path, "dSg.npy"), mmap_mode="r")
+    dMM = np.load(os.path.join(path, "dMM.npy"), mmap_mode="r")
+    X, y, theta, yerr2 = s["X"], s["y"], s["theta"], s["yerr2"]
+    B, I = theta.shape[0], s["Omega"].shape[1]
+    with threadpool_limits(1):
+        models = []
+        for b in range(B):
+            gp = go.GP(go.build_kernel(1, theta[b], X.shape[1], int(s["amp_axes"])), mean=float(s["mean"]))
+            gp.compute(X, np.sqrt(yerr2[b]))
+            gp._compute_alpha(y)
+            models.append(gp)
+        pmin = [(s["logP"][b], s["dMu"][b], dSg[b], dMM[b]) for b in range(B)]
+        Om = [[s["Omega"][b, p][:, None] for p in range(I)] for b in range(B)]
+        U = [s["U"][b] for b in range(B)]
+        reps = list(s["reps"])
+        t0 = time.perf_counter()
+        vals = [ao.information_gain(s["cand"][i], models, pmin, reps, U, Om, {"y": y}, n_innovations=I) for i in idx]
+        return time.perf_counter() - t0, vals
+
+
 def run_reference(args):
     """--impl reference: the reference path's CPU implementation (oracle port; george itself is not
     installable offline) with every host core, same metric/config, bounded sample per step."""
@@ -100,8 +161,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: N=256, D=6 (5 hyper-parameters + s), P=9, 128 walkers",
-                   "note": "george 0.4.0 cannot be installed offline; numpy/scipy oracle port of its GP path"},
+        "config": bench_config(args.gpus),
+        "note": "george 0.4.0 cannot be installed offline; numpy/scipy oracle port of its GP path",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -156,59 +217,102 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """rank / world plumbing shared by the legs."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.dev = f"cuda:{self.local}"
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok: bool) -> bool:
+        t = self.torch.tensor([1.0 if ok else 0.0], device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item() != 0.0)
+
+    def median_ms(self, fn, warm, reps):
+        """median over `reps` of the max-over-ranks duration of fn() (CUDA events, barrier before each)."""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize(); self.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            ts.append(self.max_over_ranks(a.elapsed_time(b)))
+        return float(np.median(ts))
+
+
+def peer_or_nccl(cx, eng, rows_per_rank, want):
+    """Set up the fused exchange on `eng` (all ranks agree); returns 'none' | 'peer' | 'nccl (...)'."""
+    if cx.world == 1:
+        return "none"
+    if want != "peer":
+        return "nccl"
+    try:
+        eng.peer_setup(rows_per_rank)
+        ok, why = True, ""
+    except Exception as e:                       # noqa: BLE001 -- reported in the JSON line
+        ok, why = False, str(e)[:80]
+    if cx.all_true(ok):
+        return "peer"
+    if ok:
+        eng.peer_free()
+    return f"nccl (peer mapping failed{': ' + why if why else ' on another rank'})"
+
+
+# ------------------------------------------------------------------------------------------------
+def leg_loglik(cx, args, peak_dmma, dgemm_tf):
+    """configs[1]: the headline ll+grad step (value, e2e, roofline of gp_dag_kernel, cpu_baseline)."""
+    torch, dist = cx.torch, cx.dist
     from fabolas_b200 import Engine
     from fabolas_b200.workloads import gp_workload, flops_ll, flops_llg
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    Bg = 128                                   # walkers per GPU (weak scaling)
+    rank, world = cx.rank, cx.world
+    Bg = WALKERS_PER_GPU
     w = gp_workload(CONFIG_ID, n_walkers=Bg * world)
     N, D = w["X"].shape
     d, P = D - 1, D + 3                        # P = kernel parameters + noise
-    eng = Engine(f"cuda:{local}")
+    Pk = P - 1
+    eng = Engine(cx.dev)
     eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
     theta_h = torch.from_numpy(w["theta"][rank * Bg:(rank + 1) * Bg].copy()).pin_memory()
     yerr2_h = torch.from_numpy(w["yerr2"][rank * Bg:(rank + 1) * Bg].copy()).pin_memory()
     theta_d, yerr2_d = theta_h.cuda(), yerr2_h.cuda()
-    # results of one rank packed as [grad (Bg x P) | ll (Bg)] so that ONE all-gather ships both
+    # results of one rank packed as [grad (Bg x P) | ll (Bg)] so that ONE all-gather ships both (NCCL variant)
     packed = torch.empty(Bg * P + Bg, dtype=torch.float64, device="cuda")
     g_loc, ll_loc = packed[:Bg * P].view(Bg, P), packed[Bg * P:]
     info_loc = torch.empty(Bg, dtype=torch.int32, device="cuda")
     packed_all = torch.empty(world * (Bg * P + Bg), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # 256 MB > 126 MB L2
 
-    # N > 1: the exchange of the step (every rank ends up with every walker's ll + gradient) is fused into the kernel:
-    # each CTA stores its walker's row into every rank's gather buffer over NVLink peer memory and a one-thread
-    # kernel waits for all rows (fab_gp_loglik_exchange / fab_peer_wait).  --exchange nccl keeps the kernel +
-    # NCCL all-gather pair; it is also the fallback when the peers cannot be mapped (CUDA IPC unavailable).
-    exchange = "none"
-    if world > 1:
-        exchange = args.exchange
-        if exchange == "peer":
-            try:
-                eng.peer_setup(Bg)
-            except Exception as e:                       # noqa: BLE001 -- reported in the JSON line
-                exchange = f"nccl (peer mapping failed: {str(e)[:80]})"
-            ok_all = torch.tensor([1.0 if exchange == "peer" else 0.0], device="cuda")
-            dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
-            if ok_all.item() == 0.0 and exchange == "peer":
-                exchange = "nccl (a peer could not map)"
-        if exchange == "peer":                           # one-time check against the collective it replaces
-            ll, g, info = eng.loglik(theta_d, yerr2_d, grad=True)
-            mine = torch.cat([g, ll[:, None], info.double()[:, None]], 1).contiguous()
-            ref = torch.empty(world * Bg, P + 2, dtype=torch.float64, device="cuda")
-            dist.all_gather_into_tensor(ref, mine)
+    exchange = peer_or_nccl(cx, eng, Bg, args.exchange)
+    if exchange == "peer":                           # one-time check against the collective it replaces
+        ll, g, info = eng.loglik(theta_d, yerr2_d, grad=True)
+        mine = torch.cat([g, ll[:, None], info.double()[:, None]], 1).contiguous()
+        ref = torch.empty(world * Bg, P + 2, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(ref, mine)
+        for _ in range(3):                           # three steps: both gather buffers and a reused one
             eng.loglik_exchange(theta_d, yerr2_d, grad=True)
             rows = eng.peer_wait()
             torch.cuda.synchronize()
@@ -224,26 +328,35 @@ def run_ours(args):
             dist.all_gather_into_tensor(packed_all, packed)
         return ll, g
 
-    # e2e: the walkers' parameters arrive in ONE pinned host block [theta (Bg x Pk) | yerr2 (Bg)] and the results leave
-    # in one [grad (Bg x P) | ll (Bg)]: one H2D and one D2H copy per step around the public Engine.loglik call
-    Pk = P - 1
+    # e2e: the walkers' parameters arrive in ONE pinned host block [theta (Bg x Pk) | yerr2 (Bg)]; the results leave as
+    # the rows EVERY walker of EVERY rank produced in this step ([grad | ll | info] per walker at N > 1 with the fused
+    # exchange, [grad | ll] packed otherwise): one H2D and one D2H copy per step around the public Engine call
     in_host = torch.cat([theta_h.reshape(-1), yerr2_h]).pin_memory()
     in_dev = torch.empty_like(in_host, device="cuda")
     th_view, ye_view = in_dev[:Bg * Pk].view(Bg, Pk), in_dev[Bg * Pk:]
-    out_host = torch.empty(Bg * P + Bg, dtype=torch.float64).pin_memory()
-    g_host, ll_host = out_host[:Bg * P].view(Bg, P), out_host[Bg * P:]
+    if exchange == "peer":
+        out_host = torch.empty(world * Bg, P + 2, dtype=torch.float64).pin_memory()
+    else:
+        out_host = torch.empty(world * (Bg * P + Bg), dtype=torch.float64).pin_memory()
 
     def step_e2e():
         in_dev.copy_(in_host, non_blocking=True)
-        eng.loglik(th_view, ye_view, grad=True, out=(ll_loc, g_loc, info_loc))
-        out_host.copy_(packed, non_blocking=True)
+        if exchange == "peer":
+            eng.loglik_exchange(th_view, ye_view, grad=True, out=(ll_loc, g_loc, info_loc))
+            out_host.copy_(eng.peer_wait(), non_blocking=True)
+        else:
+            eng.loglik(th_view, ye_view, grad=True, out=(ll_loc, g_loc, info_loc))
+            if world > 1:
+                dist.all_gather_into_tensor(packed_all, packed)
+                out_host.copy_(packed_all, non_blocking=True)
+            else:
+                out_host.copy_(packed, non_blocking=True)
 
     def timed(step, K, W):
         for _ in range(W):
             step()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        cx.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -252,171 +365,380 @@ def run_ours(args):
             a.record(); step(); b.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        if world > 1:
-            dist.barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall
+        cx.barrier()
+        return cx.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)), wall
 
     K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(cx.local) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_total, wall = timed(step_resident, K, W)
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed(step_e2e, K, W)
+    peer_bad = exchange == "peer" and eng.peer_error()
+    assert not peer_bad, "a peer did not deliver its rows during the timed region"
 
     # per-kernel durations (CUDA events recorded inside the library on the launching stream)
-    eng.set_timing(True)
-    kt = []
-    for _ in range(max(10, K // 2)):
-        flush.zero_()
-        eng.loglik(theta_d, yerr2_d, grad=True)
-        kt.append(eng.get_timing())
-    eng.set_timing(False)
-    ms_kernel = float(np.mean(np.array(kt)[:, 0]))        # one fused kernel per step (gp_dag_kernel, mode GRAD)
-    kt = []
-    eng.set_timing(True)
-    for _ in range(max(10, K // 2)):
-        flush.zero_()
-        eng.loglik(theta_d, yerr2_d, grad=False)
-        kt.append(eng.get_timing())
-    eng.set_timing(False)
-    ms_ll_only = float(np.mean(np.array(kt)[:, 0]))       # the MCMC inner loop proper: log-likelihood without gradient
-
-    # ---- second headline number: Entropy-Search acquisition evaluations per second (BASELINE configs[2]) ----
-    # Z = 50 representers, I = 20 innovations, 2048 candidates per GPU x 128 hyper-samples at N = 256.
-    # Setup (fit -> predict at representers -> EI -> EPMGP -> es_setup) is timed separately.
-    Z, I_, M = 50, 20, 2048
-    rng = np.random.default_rng(20260003 + rank)
-    lo = np.array([4, 4, 4, 32, -6, 1 / 256]); hi = np.array([9, 9, 9, 512, -1, 1.0])
-    reps = rng.uniform(lo, hi, (Bg, Z, D)); Omega = rng.standard_normal((Bg, I_, Z)); cand = rng.uniform(lo, hi, (M, D))
-    cand_d = eng.tensor(cand)
-
-    def es_setup():
-        eng.fit(theta_d, yerr2_d)
-        mu_r, _, cov_r = eng.predict(reps, want_var=True, want_cov=True)
-        cov_c = torch.clamp(cov_r, min=np.finfo(np.float64).eps)                  # fabolas.py:192
-        y_inc = mu_r.max(dim=1).values
-        ei_r, _, _ = eng.expected_improvement(mu_r, torch.diagonal(cov_c, dim1=1, dim2=2).contiguous(), y_inc)
-        U = torch.clamp(ei_r, min=np.finfo(np.float64).eps)
-        pm = eng.joint_min(mu_r, cov_c)
-        eng.es_setup(reps, cov_r, pm[:4], U, Omega)
-        return pm[4]
-    es_setup(); torch.cuda.synchronize()
-    t0 = time.perf_counter(); ep_info = es_setup(); torch.cuda.synchronize()
-    es_setup_ms = (time.perf_counter() - t0) * 1e3
-    for _ in range(2):
-        eng.information_gain(cand_d)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    n_ig = 5
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n_ig):
-        ig, flag = eng.information_gain(cand_d)
-    e1.record(); torch.cuda.synchronize()
-    t_ig = torch.tensor([e0.elapsed_time(e1) / n_ig], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_ig, op=dist.ReduceOp.MAX)
-    ms_ig = float(t_ig.item())
-    es_out = {"value": world * M / (ms_ig * 1e-3), "unit": "information-gain evals/s (each: 128 hyper-samples x 20 innovations, Z=50)",
-              "candidates_per_gpu": M, "ms_per_sweep": ms_ig, "setup_ms_fit_predict_ei_epmgp": es_setup_ms,
-              "nan_flags": int(flag.sum()), "epmgp_info_max": int(ep_info.max())}
-    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])       # back to the ll+grad problem state
-
-    # ---- the caller of the path: fabolas.sample_hypers' chain (fabolas.py:103-117: 100 burn-in + 500
-    # steps, 128 walkers) as ONE persistent kernel -- prior, stretch proposals, likelihood and acceptance on the device
-    from fabolas_b200._capi import FAB_PRIOR_FABOLAS
-    p0 = eng.tensor(np.random.default_rng(20260009 + rank).uniform(0, 1, (Bg, P)))
-    c_, lp_, _, _, _ = eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 20, seed=1, store_chain=False)     # warm-up
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    c_, lp_, _, _, nacc_ = eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 600, seed=2, store_chain=False)
-    e1.record(); torch.cuda.synchronize()
-    ms_mcmc = e0.elapsed_time(e1)
-    mcmc_out = {"value": (Bg + 600 * Bg) / (ms_mcmc * 1e-3), "unit": "log-prob evals/s inside one persistent sampler kernel",
-                "walkers": Bg, "steps": 600, "ms_per_chain": ms_mcmc, "us_per_half_step": ms_mcmc / 1200 * 1e3,
-                "acceptance_fraction": float(nacc_.double().mean().item() / 600),
-                "finite_log_prob": int(torch.isfinite(lp_).sum().item())}
-    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+    def kernel_ms(grad):
+        eng.set_timing(True)
+        kt = []
+        for _ in range(max(10, K // 2)):
+            flush.zero_()
+            eng.loglik(theta_d, yerr2_d, grad=grad)
+            kt.append(eng.get_timing()[0])
+        eng.set_timing(False)
+        return float(np.mean(kt))
+    ms_kernel = kernel_ms(True)            # one fused kernel per step (gp_dag_kernel, mode GRAD)
+    ms_ll_only = kernel_ms(False)          # the MCMC inner loop proper: log-likelihood without gradient
 
     # parity spot check of the timed path against the oracle (2 walkers; cheap)
     ll, g = step_resident()
     torch.cuda.synchronize()
     if rank == 0:
         from oracle import george_oracle as go
-        lo = rank * Bg
-        ref_ll, ref_g = go.loglik_batch(w["family"], w["X"], w["y"], w["mean"], w["theta"][lo:lo + 2],
-                                        w["yerr2"][lo:lo + 2], grad=True, amp_axes=int(w["amp_mult"]))
+        ref_ll, ref_g = go.loglik_batch(w["family"], w["X"], w["y"], w["mean"], w["theta"][:2], w["yerr2"][:2], grad=True,
+                                        amp_axes=int(w["amp_mult"]))
         err_ll = float(np.max(np.abs(ll[:2].cpu().numpy() - ref_ll) / np.abs(ref_ll)))
         err_g = float(np.max(np.abs(g[:2].cpu().numpy() - ref_g) / np.abs(ref_g).max(axis=1, keepdims=True)))
         assert err_ll < 1e-9 and err_g < 1e-9, (err_ll, err_g)
 
-    if rank == 0:
-        # FP64 peak: DMMA/DFMA pipe peak measured on this pool (profiles/r01_fp64_peaks.json, 36.96 TF/s),
-        # cross-checked live against cuBLAS DGEMM (library call used only as a denominator)
-        n = 4096
-        a = torch.randn(n, n, dtype=torch.float64, device="cuda"); b = torch.randn(n, n, dtype=torch.float64, device="cuda")
-        (a @ b); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); (a @ b); (a @ b); e1.record(); torch.cuda.synchronize()
-        dgemm_tf = 2 * 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
-        peak = 36.96
+    f_ll, f_llg = flops_ll(N, d), flops_llg(N, d, P)
+    kern_tf = Bg * f_llg / (ms_kernel * 1e-3) / 1e12
+    ll_tf = Bg * f_ll / (ms_ll_only * 1e-3) / 1e12
+    ms_step = ms_total / K
+    out = {
+        "value": world * Bg / (ms_step * 1e-3), "ms_per_step": ms_step,
+        "e2e": {"value": world * Bg / (ms_e2e / K * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(in_host.numel() * 8), "d2h_bytes_per_step": int(out_host.numel() * 8),
+                "what": "pinned host [theta | yerr2] -> H2D -> Engine.loglik" + ("_exchange (fused exchange)" if exchange == "peer" else "")
+                        + " -> D2H of " + ("the gathered rows of all ranks" if world > 1 else "[grad | ll]")},
+        "exchange": {"none": "none (one GPU)", "peer": "fused into the kernel: every CTA stores its walker's row into every rank's "
+                     "gather buffer over NVLink peer memory; the last CTA publishes the rank's step number to every rank and waits "
+                     "for every rank's -- one launch per step, no collective"}.get(exchange, "NCCL all-gather after the kernel [" + exchange + "]"),
+        "gpu_launches": K,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "pipe": "FP64 tensor cores (DMMA mma.sync m8n8k4.f64; tcgen05 has no FP64 kind)",
+                     "kernel": "gp_dag_kernel", "achieved": kern_tf, "peak": peak_dmma,
+                     "unit": "TFLOP/s", "frac": kern_tf / peak_dmma, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                     "traffic_source": TRAFFIC_SOURCE,
+                     "peak_source": "measured DMMA m8n8k4 peak on this pool (profiles/r01_fp64_peaks.json); "
+                                    "MEASURED_PEAKS.json carries no FP64 figure",
+                     "peak_cublas_dgemm_live": dgemm_tf, "frac_vs_cublas_dgemm_live": kern_tf / dgemm_tf,
+                     "flops_per_eval": f_llg, "evals_per_launch": Bg, "ms_per_launch": ms_kernel,
+                     "ll_only": {"evals_per_s": Bg / (ms_ll_only * 1e-3), "ms_per_launch": ms_ll_only,
+                                 "flops_per_eval": f_ll, "achieved": ll_tf, "frac": ll_tf / peak_dmma},
+                     "whole_step_frac": Bg * f_llg / (ms_step * 1e-3) / 1e12 / peak_dmma},
+        "wall_s_timed_region": wall,
+    }
+    if exchange == "peer":
+        eng.peer_free()
+    return out, eng, w, theta_d, yerr2_d
+
+
+def leg_es(cx, args, eng, w, theta_d, yerr2_d, peak_dfma):
+    """configs[2]: Entropy-Search acquisition -- Z = 50 representers, I = 20 innovations, 2048 candidates per GPU x 128
+    hyper-samples at N = 256.  Setup (fit -> predict at representers -> EI -> EPMGP -> es_setup) is timed separately."""
+    torch = cx.torch
+    Bg, D = WALKERS_PER_GPU, w["D"]
+    Z, I_, M = 50, 20, 2048
+    rng = np.random.default_rng(20260003 + cx.rank)
+    lo = np.array([4, 4, 4, 32, -6, 1 / 256]); hi = np.array([9, 9, 9, 512, -1, 1.0])
+    reps = rng.uniform(lo, hi, (Bg, Z, D)); Omega = rng.standard_normal((Bg, I_, Z)); cand = rng.uniform(lo, hi, (M, D))
+    cand_h = torch.from_numpy(cand).pin_memory()
+    cand_d = eng.tensor(cand)
+    eps = np.finfo(np.float64).eps
+    keep = {}
+
+    def es_setup():
+        eng.fit(theta_d, yerr2_d)
+        mu_r, _, cov_r = eng.predict(reps, want_var=True, want_cov=True)
+        cov_c = torch.clamp(cov_r, min=eps)                                       # fabolas.py:192
+        y_inc = mu_r.max(dim=1).values
+        ei_r, _, _ = eng.expected_improvement(mu_r, torch.diagonal(cov_c, dim1=1, dim2=2).contiguous(), y_inc)
+        U = torch.clamp(ei_r, min=eps)
+        pm = eng.joint_min(mu_r, cov_c)
+        eng.es_setup(reps, cov_r, pm[:4], U, Omega)
+        keep.update(pm=pm, U=U, mu=mu_r, cov=cov_c)
+        return pm[4]
+    es_setup(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); ep_info = es_setup(); torch.cuda.synchronize()
+    es_setup_ms = (time.perf_counter() - t0) * 1e3
+    eng.set_timing(True)
+    eng.joint_min(keep["mu"], keep["cov"]); ep_ms = eng.get_timing()
+    eng.set_timing(False)
+
+    n_ig = 5
+    ms_ig = cx.median_ms(lambda: eng.information_gain(cand_d), 2, n_ig)
+    ig, flag = eng.information_gain(cand_d)
+    # e2e: candidates in pinned host memory -> H2D -> information gain -> D2H of ig and the NaN flags
+    cand_in = torch.empty_like(cand_d)
+    ig_host = torch.empty(M, dtype=torch.float64).pin_memory()
+    flag_host = torch.empty(M, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        cand_in.copy_(cand_h, non_blocking=True)
+        g_, f_ = eng.information_gain(cand_in)
+        ig_host.copy_(g_, non_blocking=True); flag_host.copy_(f_, non_blocking=True)
+    ms_e2e = cx.median_ms(step_e2e, 2, n_ig)
+    # per-kernel durations of one sweep: [gp_predict_kernel, es_mix_kernel, es_entropy_kernel, es_reduce_kernel]
+    eng.set_timing(True)
+    kt = []
+    for _ in range(n_ig):
+        eng.information_gain(cand_d); kt.append(eng.get_timing())
+    eng.set_timing(False)
+    kt = np.mean(np.array(kt), axis=0)
+    # es_entropy_kernel against the FP64 issue rate: every (candidate, model, innovation, column, row) element costs
+    # ES_FP64_INSTR_PER_ELEMENT FP64-pipe instructions (one exp each); the DFMA microbenchmark peak / 2 is the rate at
+    # which the chip issues FP64 instructions
+    elements = float(M) * Bg * I_ * Z * Z
+    fp64_instr = ES_FP64_INSTR_PER_ELEMENT * elements
+    achieved = fp64_instr / (kt[2] * 1e-3) / 1e12            # T FP64-instr/s
+    peak_issue = peak_dfma / 2.0
+    out = {"metric": "ES acquisition evals/sec (Z=50 representers, I=20 innovations, 128 hyper-samples, N=256)",
+           "value": cx.world * M / (ms_ig * 1e-3), "unit": "information-gain evals/s",
+           "candidates_per_gpu": M, "ms_per_sweep": ms_ig, "gpu_launches_per_sweep": 4,
+           "e2e": {"value": cx.world * M / (ms_e2e * 1e-3), "unit": "information-gain evals/s",
+                   "h2d_bytes_per_step": int(cand_h.numel() * 8), "d2h_bytes_per_step": int(M * 8 + M * 4),
+                   "what": "pinned host candidates -> H2D -> Engine.information_gain -> D2H of ig + NaN flags"},
+           "roofline": {"bound": "fp64-issue", "kernel": "es_entropy_kernel", "achieved": achieved, "peak": peak_issue,
+                        "unit": "T FP64 instr/s", "frac": achieved / peak_issue, "traffic": ES_TRAFFIC_BYTES_PER_LAUNCH,
+                        "traffic_source": ES_TRAFFIC_SOURCE,
+                        "fp64_instr_per_element": ES_FP64_INSTR_PER_ELEMENT, "elements_per_launch": elements,
+                        "ms_per_launch": float(kt[2]),
+                        "peak_source": "measured DFMA peak / 2 flops (profiles/r01_fp64_peaks.json): one FP64 instruction "
+                                       "per lane and issue slot of the FP64 pipe",
+                        "kernel_share_of_sweep": float(kt[2] / kt.sum())},
+           "kernel_ms": {"gp_predict_kernel": float(kt[0]), "es_mix_kernel": float(kt[1]), "es_entropy_kernel": float(kt[2]),
+                         "es_reduce_kernel": float(kt[3]), "epmgp_ep_kernel(setup)": float(ep_ms[0]),
+                         "epmgp_normalize_kernel(setup)": float(ep_ms[1])},
+           "setup_ms_fit_predict_ei_epmgp": es_setup_ms,
+           "nan_flags": int(flag.sum()), "epmgp_info_max": int(ep_info.max())}
+    # CPU baseline: the oracle port of acquisitions.information_gain on the same prepared lists, a few candidates per core
+    if cx.world == 1 and cx.rank == 0 and not args.no_cpu:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        per_core = args.es_cpu_per_core
+        tmp = tempfile.mkdtemp(prefix="fab_es_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")) as f:
-                peak = max(v for k, v in json.load(f).items() if k.startswith("dmma_m8n8k4"))
-        except Exception:
-            pass
-        f_ll, f_llg = flops_ll(N, d), flops_llg(N, d, P)
-        kern_tf = Bg * f_llg / (ms_kernel * 1e-3) / 1e12
-        ll_tf = Bg * f_ll / (ms_ll_only * 1e-3) / 1e12
-        cpu_val, cores, n_evals, cpu_dt = (None, None, None, None)
-        if world == 1 and not args.no_cpu:
-            cpu_val, cores, n_evals, cpu_dt = cpu_oracle_rate(per_core=args.cpu_per_core)
-        ms_step = ms_total / K
-        out = {
-            "metric": METRIC, "value": world * Bg / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: CNN-CIFAR10 space (5 hyper-parameters) + s, N=256, D=6, P=9, "
-                                   "128 walkers per GPU, Matern52 x (linear+const) basis kernel",
-                       "walkers_per_gpu": Bg, "N": N, "D": D, "l2_flush_between_steps": True,
-                       "parallelism": f"walkers sharded x{world}; exchange of the per-walker (grad | ll | info) rows per step: "
-                                      + {"none": "none (one GPU)", "peer": "fused into the kernel (NVLink peer stores into every "
-                                         "rank's gather buffer + arrival counter; one-thread wait kernel)"}.get(
-                                             exchange, "NCCL all-gather after the kernel [" + exchange + "]")},
-            "e2e": {"value": world * Bg / (ms_e2e / K * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(in_host.numel() * 8),
-                    "d2h_bytes_per_step": int(out_host.numel() * 8)},
-            "gpu_launches": K * (2 if exchange == "peer" else 1),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "pipe": "FP64 tensor cores (DMMA mma.sync m8n8k4.f64; tcgen05 has no FP64 kind)",
-                         "kernel": "gp_dag_kernel", "achieved": kern_tf, "peak": peak,
-                         "unit": "TFLOP/s", "frac": kern_tf / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
-                         "traffic_source": TRAFFIC_SOURCE,
-                         "peak_source": "measured DMMA m8n8k4 peak on this pool (profiles/r01_fp64_peaks.json); "
-                                        "MEASURED_PEAKS.json carries no FP64 figure; "
-                                        f"live cuBLAS DGEMM 4096^3 = {dgemm_tf:.2f} TFLOP/s",
-                         "flops_per_eval": f_llg, "evals_per_launch": Bg, "ms_per_launch": ms_kernel,
-                         "ll_only": {"evals_per_s": Bg / (ms_ll_only * 1e-3), "ms_per_launch": ms_ll_only,
-                                     "flops_per_eval": f_ll, "achieved": ll_tf, "frac": ll_tf / peak},
-                         "whole_step_frac": Bg * f_llg / (ms_step * 1e-3) / 1e12 / peak},
-            "es_acquisition": es_out,
-            "mcmc_device_sampler": mcmc_out,
-            "cpu_baseline": None if cpu_val is None else {
-                "value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{n_evals} ll+grad evals of the same workload, one single-threaded numpy/scipy oracle "
-                          f"process per core, {cpu_dt:.1f} s wall"},
-            "wall_s_timed_region": wall,
-        }
-        print(json.dumps(out))
+            pm = keep["pm"]
+            np.savez(os.path.join(tmp, "small.npz"), X=w["X"], y=w["y"], theta=w["theta"][:Bg], yerr2=w["yerr2"][:Bg],
+                     mean=w["mean"], amp_axes=int(w["amp_mult"]), reps=reps, Omega=Omega, cand=cand,
+                     U=keep["U"].cpu().numpy(), logP=pm[0].cpu().numpy(), dMu=pm[1].cpu().numpy())
+            np.save(os.path.join(tmp, "dSg.npy"), pm[2].cpu().numpy())
+            np.save(os.path.join(tmp, "dMM.npy"), pm[3].cpu().numpy())
+            jobs = [(tmp, list(range(i * per_core, (i + 1) * per_core))) for i in range(cores)]
+            with mp.get_context("spawn").Pool(cores) as pool:
+                res = pool.map(_es_cpu_worker, jobs)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        t_max = max(r[0] for r in res)
+        ref = np.concatenate([r[1] for r in res])
+        n = len(ref)
+        got = ig[:n].cpu().numpy()
+        err = float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))))
+        assert err < 1e-6, f"information gain differs from the CPU oracle: {err}"
+        out["cpu_baseline"] = {"value": n / t_max, "unit": "information-gain evals/s", "cores": cores, "kind": "port",
+                               "sample": f"{n} of the {M} candidates ({per_core} per core), each against all {Bg} hyper-samples x "
+                                         f"{I_} innovations: oracle port of acquisitions.information_gain (acq_oracle.py), one "
+                                         f"single-threaded process per core, slowest worker {t_max:.1f} s (model setup untimed)",
+                               "max_rel_err_gpu_vs_oracle": err}
+    return out
+
+
+def leg_mcmc(cx, eng, w):
+    """The caller of the path: fabolas.sample_hypers' chain (fabolas.py:103-117: 100 burn-in + 500 steps,
+    128 walkers) as ONE persistent kernel -- prior, stretch proposals, likelihood and acceptance on the device."""
+    torch = cx.torch
+    from fabolas_b200._capi import FAB_PRIOR_FABOLAS
+    Bg, P = WALKERS_PER_GPU, w["D"] + 3
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+    p0 = eng.tensor(np.random.default_rng(20260009 + cx.rank).uniform(0, 1, (Bg, P)))
+    eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 20, seed=1, store_chain=False)     # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    c_, lp_, _, _, nacc_ = eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 600, seed=2, store_chain=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": (Bg + 600 * Bg) / (ms * 1e-3), "unit": "log-prob evals/s inside one persistent sampler kernel",
+            "walkers": Bg, "steps": 600, "ms_per_chain": ms, "us_per_half_step": ms / 1200 * 1e3,
+            "acceptance_fraction": float(nacc_.double().mean().item() / 600),
+            "finite_log_prob": int(torch.isfinite(lp_).sum().item())}
+
+
+def leg_configs(cx, args, peak_dmma):
+    """The other BASELINE.json configurations and the multi-GPU checks, at whatever N this run has."""
+    torch, dist = cx.torch, cx.dist
+    from fabolas_b200 import Engine, dist as fd
+    from fabolas_b200._capi import FAB_PRIOR_FABOLAS
+    from fabolas_b200.workloads import gp_workload, flops_ll, flops_llg
+    rank, world = cx.rank, cx.world
+    out = {}
+
+    # ---- configs[0]: the reference's own shape (svm_mnist: N = 100, 20 walkers); one GPU's work, every rank runs it ----
+    w = gp_workload(1)
+    eng = Engine(cx.dev)
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+    th, ye = eng.tensor(w["theta"]), eng.tensor(w["yerr2"])
+    N, d, P = w["N"], w["D"] - 1, w["theta"].shape[1] + 1
+    c0 = {"N": N, "walkers": 20}
+    for grad in (False, True):
+        ms = cx.median_ms(lambda: eng.loglik(th, ye, grad=grad), 5, 30)
+        F = flops_llg(N, d, P) if grad else flops_ll(N, d)
+        tf = F * 20 / (ms * 1e-3) / 1e12
+        c0["ll+grad" if grad else "ll"] = {"us_per_batch": ms * 1e3, "evals_per_s": 20 / (ms * 1e-3), "tflops": tf,
+                                           "frac_fp64_tensor_peak": tf / peak_dmma,
+                                           "frac_of_the_20_busy_sms": tf / (peak_dmma * 20 / 148)}
+    p0 = eng.tensor(np.random.default_rng(5).uniform(0, 1, (20, P)))
+    eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 10, seed=1, store_chain=False)
+    ms = cx.median_ms(lambda: eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.clone(), 600, seed=2, store_chain=False), 0, 3)
+    c0["sample_hypers_chain"] = {"steps": 600, "ms_per_chain": ms, "us_per_half_step": ms / 1200 * 1e3,
+                                 "what": "fabolas.sample_hypers' 100 + 500 stretch-move steps, 20 walkers, one persistent kernel"}
+    out["configs[0] svm_mnist shape"] = c0
+    eng.close()
+
+    # ---- configs[3]: 1M candidates at N = 512 sharded over the GPUs: predict + EI + argmax, one (value, index) pair
+    # per rank exchanged; the winner must be the single-GPU argmax ----
+    w = gp_workload(4, n_walkers=1)
+    eng = Engine(cx.dev)
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+    eng.fit(w["theta"], w["yerr2"])
+    M = 1 << 20
+    T = np.random.default_rng(7).uniform(w["X"].min(0), w["X"].max(0), (M, w["D"]))
+    lo, hi = fd.shard_range(M, rank, world)
+    Td = eng.tensor(T[lo:hi])
+    y_max = float(w["y"].max())
+    res = {}
+    # the timed sweep keeps the shard resident (fd.sharded_ei_argmax copies the candidates from the host on each call)
+    ymax_d = eng.tensor(np.array([y_max]))
+
+    def sweep():
+        mu, var = eng.predict(Td, want_var=True)
+        _, bv, bi = eng.expected_improvement(mu[:1], var[:1], ymax_d, want_ei=False)
+        res["best"] = fd.sharded_argmax_pair(float(bv[0]), int(bi[0]) + lo, eng.device)
+    ms = cx.median_ms(sweep, 2, 5)
+    eng.set_timing(True); eng.predict(Td, want_var=True); ms_pred = cx.max_over_ranks(eng.get_timing()[0]); eng.set_timing(False)
+    Tfull = eng.tensor(T)
+    mu, var = eng.predict(Tfull, want_var=True)
+    _, bv1, bi1 = eng.expected_improvement(mu[:1], var[:1], ymax_d, want_ei=False)
+    same = cx.all_true(int(bi1[0]) == res["best"][1] and float(bv1[0]) == res["best"][0])
+    F = w["N"] ** 2 + w["N"] * (3 * (w["D"] - 1) + 38)
+    tf = F * M / (ms * 1e-3) / 1e12
+    out["configs[3] 1M-candidate sweep"] = {
+        "N": w["N"], "candidates": M, "n_gpus": world, "ms_per_sweep": ms, "candidates_per_s": M / (ms * 1e-3),
+        "tflops_aggregate": tf, "frac_fp64_tensor_peak": tf / (peak_dmma * world),
+        "argmax_index": res["best"][1], "sharded_argmax_equals_single_gpu_argmax": same,
+        "exchange": "one (value, index) pair per rank, NCCL all-gather" if world > 1 else "none (one GPU)"}
+    assert same, "sharded argmax differs from the single-GPU argmax"
+    del Tfull, mu, var
+    eng.close()
+
+    # ---- configs[4]: N = 2048, 128 walkers per GPU (1024 on 8), ll and ll+grad, the step's exchange included ----
+    Bg = WALKERS_PER_GPU
+    w = gp_workload(5, n_walkers=Bg * world)
+    eng = Engine(cx.dev)
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+    th, ye = eng.tensor(w["theta"][rank * Bg:(rank + 1) * Bg]), eng.tensor(w["yerr2"][rank * Bg:(rank + 1) * Bg])
+    exchange = peer_or_nccl(cx, eng, Bg, args.exchange)
+    N, d, P = w["N"], w["D"] - 1, w["theta"].shape[1] + 1
+    c4 = {"N": N, "walkers": Bg * world, "n_gpus": world, "exchange": exchange}
+    for grad in (False, True):
+        def step():
+            if exchange == "peer":
+                eng.loglik_exchange(th, ye, grad=grad); eng.peer_wait()
+            else:
+                o = eng.loglik(th, ye, grad=grad)
+                if world > 1:
+                    mine = torch.cat(([o[1]] if grad else []) + [o[0][:, None]], 1).contiguous()
+                    dist.all_gather_into_tensor(torch.empty(world * Bg, mine.shape[1], dtype=torch.float64, device="cuda"), mine)
+        ms = cx.median_ms(step, 1, 3)
+        o = eng.loglik(th, ye, grad=grad)
+        F = flops_llg(N, d, P) if grad else flops_ll(N, d)
+        tf = F * Bg * world / (ms * 1e-3) / 1e12
+        c4["ll+grad" if grad else "ll"] = {"ms_per_batch": ms, "evals_per_s": Bg * world / (ms * 1e-3), "tflops_aggregate": tf,
+                                           "frac_fp64_tensor_peak": tf / (peak_dmma * world),
+                                           "finite_ll": cx.all_true(bool(torch.isfinite(o[0]).all()))}
+    if exchange == "peer":
+        c4["peer_error"] = bool(eng.peer_error())
+        eng.peer_free()
+    out["configs[4] N=2048"] = c4
+    eng.close()
+
+    # ---- sharded device sampler: chain dealt to the ranks must be bit-identical to the single-GPU chain ----
     if world > 1:
-        dist.destroy_process_group()
+        w = gp_workload(2)
+        eng = Engine(cx.dev)
+        eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+        K, P = Bg * world, eng.Pk + 1
+        p0 = np.random.default_rng(11).uniform(0, 1, (K, P))
+        nsteps = 8
+        ref_c, ref_lp, _, _, ref_n = eng.mcmc_run(FAB_PRIOR_FABOLAS, p0.copy(), nsteps, seed=5, store_chain=False)
+        torch.cuda.synchronize()
+        try:
+            eng.mcmc_peer_setup(K, P)
+            ok_setup = True
+        except Exception:                            # noqa: BLE001
+            ok_setup = False
+        if cx.all_true(ok_setup):
+            c, lp, n = eng.mcmc_run_sharded(FAB_PRIOR_FABOLAS, p0.copy(), 3, seed=5)
+            c, lp, n = eng.mcmc_run_sharded(FAB_PRIOR_FABOLAS, c, nsteps - 3, log_prob=lp, seed=5, iter0=3, naccepted=n)
+            torch.cuda.synchronize()
+            err = eng.mcmc_peer_error()
+            dist.all_reduce(n)                       # accepted moves are counted on the owning rank
+            same = cx.all_true(bool(torch.equal(c, ref_c) and torch.equal(lp, ref_lp) and torch.equal(n, ref_n)) and not err)
+            steps = 30
+            t1 = cx.median_ms(lambda: eng.mcmc_run(FAB_PRIOR_FABOLAS, ref_c.clone(), steps, log_prob=ref_lp.clone(), seed=6,
+                                                   store_chain=False), 1, 3)
+            tm = cx.median_ms(lambda: eng.mcmc_run_sharded(FAB_PRIOR_FABOLAS, c, steps, log_prob=lp, seed=6), 1, 3)
+            out["sharded device sampler"] = {"walkers": K, "n_gpus": world, "bit_identical_to_single_gpu_chain": same,
+                                             "us_per_half_step_one_gpu": t1 / (2 * steps) * 1e3,
+                                             "us_per_half_step_sharded": tm / (2 * steps) * 1e3, "peer_error": bool(err)}
+            assert same, "sharded sampler chain differs from the single-GPU chain"
+            eng.mcmc_peer_free()
+        else:
+            out["sharded device sampler"] = {"skipped": "peer mapping failed"}
+        eng.close()
+    return out
+
+
+def run_ours(args):
+    cx = Ctx(args)
+    torch = cx.torch
+    peak_dmma, peak_dfma = fp64_peaks()
+    # live cuBLAS DGEMM (library call used only as a second denominator, outside every timed region)
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda"); b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    (a @ b); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); (a @ b); (a @ b); e1.record(); torch.cuda.synchronize()
+    dgemm_tf = 2 * 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b
+
+    main, eng, w, theta_d, yerr2_d = leg_loglik(cx, args, peak_dmma, dgemm_tf)
+    es_out = leg_es(cx, args, eng, w, theta_d, yerr2_d, peak_dfma)
+    mcmc_out = leg_mcmc(cx, eng, w)
+    eng.close()
+    cfgs = {} if args.no_configs else leg_configs(cx, args, peak_dmma)
+
+    if cx.rank == 0:
+        cpu = None
+        if cx.world == 1 and not args.no_cpu:
+            cpu_val, cores, n_evals, cpu_dt = cpu_oracle_rate(per_core=args.cpu_per_core)
+            cpu = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n_evals} ll+grad evals of the same workload, one single-threaded numpy/scipy oracle "
+                             f"process per core, {cpu_dt:.1f} s wall"}
+        out = {"metric": METRIC, "value": main.pop("value"), "unit": UNIT, "n_gpus": cx.world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": main.pop("ms_per_step"), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": bench_config(cx.world)}
+        out.update(main)
+        out["es_acquisition"] = es_out
+        out["mcmc_device_sampler"] = mcmc_out
+        out["configs"] = cfgs
+        out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 def main():
@@ -427,9 +749,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-walker results reach every rank (fused peer stores, or NCCL all-gather)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline legs (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (profiling runs)")
     ap.add_argument("--cpu-per-core", type=int, default=640,
                     help="ll+grad evaluations per host core of the bounded CPU-oracle sample (~10-30 s of CPU work)")
+    ap.add_argument("--es-cpu-per-core", type=int, default=8,
+                    help="information-gain evaluations per host core of the bounded CPU-oracle sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -158,8 +158,8 @@ class Engine:
 
     def get_timing(self):
         """Durations (ms) of the kernels launched by the most recent batched call."""
-        buf = (_c_dbl * 4)()
-        n = self.lib.fab_ctx_get_timing(self._ctx, buf, 4)
+        buf = (_c_dbl * 8)()
+        n = self.lib.fab_ctx_get_timing(self._ctx, buf, 8)
         if n < 0:
             self._check(n, "fab_ctx_get_timing")
         return [buf[i] for i in range(n)]

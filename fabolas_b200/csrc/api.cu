@@ -16,6 +16,8 @@
 
 using namespace fab;
 
+constexpr int FAB_NEV = 8;      // events of the optional per-kernel timing: up to 7 intervals per call
+
 struct fab_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -76,7 +78,7 @@ struct fab_ctx {
     int mcmc_max_ctas = 0;       // test knob: cap the sampler's grid (0 = one CTA per proposal, up to the SM count)
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[FAB_NEV] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int ev_used = 0;        // number of intervals recorded by the last call
 };
 
@@ -94,6 +96,13 @@ int fail(fab_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     do {                                                                       \
         cudaError_t e_ = (call);                                               \
         if (e_ != cudaSuccess) return fail((c), FAB_ECUDA, #call, e_);         \
+    } while (0)
+
+// optional per-kernel timing: mark(c, i) records event i on the stream (i = 0 before the first launch of a call,
+// i = k after the k-th); the call ends with marks_done(c, k)
+#define FAB_MARK(c, i)                                                         \
+    do {                                                                       \
+        if ((c)->timing) FAB_CUDA((c), cudaEventRecord((c)->ev[(i)], (c)->stream)); \
     } while (0)
 
 template <typename T>
@@ -181,7 +190,7 @@ int fab_ctx_destroy(fab_ctx* c) {
     cudaFree(c->sc_mu); cudaFree(c->sc_var); cudaFree(c->sc_dot); cudaFree(c->sc_c0); cudaFree(c->sc_part);
     cudaFree(c->sc_vmix); cudaFree(c->sc_mmix);
 #ifndef FAB_CUSIM
-    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < FAB_NEV; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 #endif
     for (auto& kv : c->dag) { cudaFree(kv.second.bulk); cudaFree(kv.second.chain); }
     cudaFree(c->wkSpill);
@@ -224,7 +233,7 @@ int fab_ctx_set_timing(fab_ctx* c, int enable) {
     if (!c) return FAB_EINVAL;
 #ifndef FAB_CUSIM
     if (enable && !c->ev[0])
-        for (int i = 0; i < 4; ++i) FAB_CUDA(c, cudaEventCreate(&c->ev[i]));
+        for (int i = 0; i < FAB_NEV; ++i) FAB_CUDA(c, cudaEventCreate(&c->ev[i]));
 #endif
     c->timing = enable != 0;
     c->ev_used = 0;
@@ -435,10 +444,14 @@ int fab_epmgp_joint_min_batch(fab_ctx* c, const double* mu, const double* Sigma,
     EpArgs a;
     a.mu = mu; a.Sigma = Sigma; a.Z = Z; a.logP = logP; a.dMu = dMu; a.dSigma = dSigma; a.dMuMu = dMuMu;
     a.info = info; a.sweeps = sweeps; a.with_derivatives = wd;
+    FAB_MARK(c, 0);
     FAB_LAUNCH(epmgp_ep_kernel, dim3(Z, B), EP_THREADS, ep_smem_bytes(Z), c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
+    FAB_MARK(c, 1);
     FAB_LAUNCH(epmgp_normalize_kernel, B, 256, ep_norm_smem_bytes(Z), c->stream, a);
     FAB_CUDA(c, cudaGetLastError());
+    FAB_MARK(c, 2);
+    if (c->timing) c->ev_used = 2;          // [epmgp_ep_kernel, epmgp_normalize_kernel]
     return FAB_OK;
 }
 
@@ -501,20 +514,26 @@ int fab_es_information_gain_batch(fab_ctx* c, const double* Xc, int M, double* i
     if ((rc = ensure(c, &c->sc_part, &c->cap_sc[4], (size_t)B * M)) != FAB_OK) return rc;
     if ((rc = ensure(c, &c->sc_vmix, &c->cap_sc[5], (size_t)M)) != FAB_OK) return rc;
     if ((rc = ensure(c, &c->sc_mmix, &c->cap_sc[6], (size_t)M)) != FAB_OK) return rc;
+    FAB_MARK(c, 0);
     rc = launch_predict(c, Xc, 0, M, c->sc_mu, c->sc_var, nullptr, c->es.vrl, c->sc_dot);
     if (rc != FAB_OK) return rc;
+    FAB_MARK(c, 1);
     EsMixArgs m;
     m.gd = gd; m.theta = c->dTheta; m.yerr2 = c->dYerr2; m.st = c->es; m.Xc = Xc; m.M = M; m.B = B;
     m.mu = c->sc_mu; m.var = c->sc_var; m.dot = c->sc_dot; m.vmix = c->sc_vmix; m.mmix = c->sc_mmix; m.c0 = c->sc_c0;
     FAB_LAUNCH(es_mix_kernel, M, ES_THREADS, 0, c->stream, m);
     FAB_CUDA(c, cudaGetLastError());
+    FAB_MARK(c, 2);
     EsEntropyArgs e;
     e.st = c->es; e.M = M; e.B = B; e.vmix = c->sc_vmix; e.c0 = c->sc_c0; e.partial = c->sc_part;
     FAB_LAUNCH(es_entropy_kernel, dim3((M + ES_XPB - 1) / ES_XPB, B), ES_THREADS,
                es_entropy_smem_bytes(c->es.Z, c->es.I), c->stream, e);
     FAB_CUDA(c, cudaGetLastError());
+    FAB_MARK(c, 3);
     FAB_LAUNCH(es_reduce_kernel, (M + 127) / 128, 128, 0, c->stream, c->sc_part, M, B, ig, nan_flag);
     FAB_CUDA(c, cudaGetLastError());
+    FAB_MARK(c, 4);
+    if (c->timing) c->ev_used = 4;          // [gp_predict_kernel, es_mix_kernel, es_entropy_kernel, es_reduce_kernel]
     if (mix_mean) FAB_CUDA(c, cudaMemcpyAsync(mix_mean, c->sc_mmix, sizeof(double) * M, cudaMemcpyDeviceToDevice, c->stream));
     if (mix_var) FAB_CUDA(c, cudaMemcpyAsync(mix_var, c->sc_vmix, sizeof(double) * M, cudaMemcpyDeviceToDevice, c->stream));
     return FAB_OK;

@@ -51,7 +51,8 @@ const char* fab_last_error(const fab_ctx* ctx);
 /* Optional per-kernel timing for benchmarks: when enabled, every batched call records CUDA events
  * around each of its kernel launches on the context's stream.  fab_ctx_get_timing synchronises on
  * the last event and writes the durations (ms) of the kernels of the most recent call, in launch
- * order (loglik: [factor, gradient]); returns the number of intervals or a negative code.        */
+ * order (loglik / fit / mcmc: [the one fused kernel]; joint_min: [ep, normalize]; information gain:
+ * [predict, mix, entropy, reduce]); returns the number of intervals (<= 7) or a negative code.     */
 int fab_ctx_set_timing(fab_ctx* ctx, int enable);
 int fab_ctx_get_timing(fab_ctx* ctx, double* ms_out, int n);
 
