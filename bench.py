@@ -617,7 +617,6 @@ def leg_configs(cx, args, peak_dmma):
         _, bv, bi = eng.expected_improvement(mu[:1], var[:1], ymax_d, want_ei=False)
         res["best"] = fd.sharded_argmax_pair(float(bv[0]), int(bi[0]) + lo, eng.device)
     ms = cx.median_ms(sweep, 2, 5)
-    eng.set_timing(True); eng.predict(Td, want_var=True); ms_pred = cx.max_over_ranks(eng.get_timing()[0]); eng.set_timing(False)
     Tfull = eng.tensor(T)
     mu, var = eng.predict(Tfull, want_var=True)
     _, bv1, bi1 = eng.expected_improvement(mu[:1], var[:1], ymax_d, want_ei=False)

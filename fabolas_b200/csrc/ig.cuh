@@ -148,23 +148,71 @@ struct EsEntropyArgs {
     double* partial;      // M x B   per-model information gain (already averaged over innovations and columns)
 };
 
-// grid (ceil(M / ES_XPB), B): one model, ES_XPB candidates per CTA; warp w takes innovations w, w+4, ...
+// exp() of the entropy kernel: e^t / 2^qref for any finite t, exponent handled with integer arithmetic.
+//   n = round(t * 256 / ln2) = 256 q + j ;  e^t = 2^q * 2^(j/256) * e^rr ,  rr = t - n ln2/256 , |rr| <= ln2/512
+//   2^(j/256) from a 256-entry table, e^rr by a degree-4 Taylor polynomial (remainder 3.8e-17), and the power of two
+//   2^(q - qref) added straight into the exponent field -- the reference shift of the log-sum-exp costs no FP64
+//   instruction.  11 FP64-pipe instructions per element with the two accumulations (t itself is the twelfth).
+// The table is replicated over the 16 bank pairs of shared memory (entry j of lane l at tab[16 j + (l & 15)]): lanes
+// pick arbitrary entries, and without the replication the look-ups serialise ~5-fold on bank conflicts.
+constexpr int ES_TAB_N = 256;
+constexpr int ES_TAB_REPL = 16;
+constexpr int ES_NC = 4;            // columns per thread and pass: independent chains, broadcasts of det / sdm amortised
+__device__ __forceinline__ double es_exp_scaled(double t, int qref, const double* __restrict__ tab_lane) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double T = fma(t, 369.32993046757462, MAGIC);      // 256 / ln2
+    const double nd = T - MAGIC;
+    const int n = (int)(__double_as_longlong(T) & 0xffffffffLL);
+    double rr = fma(nd, -2.70760617331688990816e-03, t);     // ln2_hi / 256 (32 significant bits: nd * hi exact)
+    rr = fma(nd, -7.45396456746323320320e-13, rr);           // ln2_lo / 256
+    double p = 4.1666666666666664e-02;                       // 1/4!
+    p = fma(p, rr, 1.6666666666666666e-01);
+    p = fma(p, rr, 0.5);
+    p = fma(p, rr, 1.0);
+    p = fma(p, rr, 1.0);
+    const double v = tab_lane[(n & (ES_TAB_N - 1)) * ES_TAB_REPL] * p;
+    const int dq = (n >> 8) - qref;                          // <= 0 by the choice of qref; < -1000: below 2^-1000 of the reference
+    const double w = __longlong_as_double(__double_as_longlong(v) + ((long long)dq << 52));
+    return (dq >= -1000) ? w : 0.0;
+}
+
+// One column the careful way (exact maximum first, polynomial exp without tables): the path of columns whose sums
+// left the range of the fast path, and of inputs that are not finite -- those must surface as NaN (nan_flag).
+__device__ __noinline__ double es_column_exact(double o, const double2* __restrict__ sd, int Z) {
+    double mx = -INFINITY;
+    for (int q = 0; q < Z; ++q) mx = fmax(mx, fma(sd[q].x, o, sd[q].y));
+    double se = 0.0, sw = 0.0;
+    for (int q = 0; q < Z; ++q) {
+        const double t = fma(sd[q].x, o, sd[q].y);
+        const double d = t - mx;
+        const double e = (d == d) ? exp_nonpos(d) : d;       // t <= mx; a non-finite t makes the sums NaN
+        se += e; sw = fma(e, t, sw);
+    }
+    return sw / se - (mx + log(se));
+}
+
+// grid (ceil(M / ES_XPB), B): one model, ES_XPB candidates per CTA; the I * Z columns (innovation p, column bb) of a
+// candidate are dealt to the threads, ES_NC per thread and pass.
 __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a) {
     FAB_DYN_SMEM(smem_raw);
     const int Z = a.st.Z, I = a.st.I, b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = ES_THREADS / 32;
-    double* coef = reinterpret_cast<double*>(smem_raw);     // 8 x Z
+    double* etab = reinterpret_cast<double*>(smem_raw);     // ES_TAB_N x ES_TAB_REPL (first: 128-byte rows stay aligned)
+    double* coef = etab + ES_TAB_N * ES_TAB_REPL;           // 8 x Z
     double* logU = coef + 8 * Z;                            // Z
     double* om = logU + Z;                                  // I x Z
-    double* det = om + (size_t)I * Z;                       // Z
-    double* sdm = det + Z;                                  // Z
-    double* red = sdm + Z;                                  // nw (8 reserved)
-    double* etab = red + 8;                                 // exp table of exp_neg_fast
-    exp_table_fill(etab);
+    double2* sd = reinterpret_cast<double2*>(om + (size_t)((I * Z + 1) & ~1));   // Z x (sdm, det)
+    double* red = reinterpret_cast<double*>(sd + Z);        // nw, then [8] smax, [9] dmax, [10] inputs finite, [11] max |det|
+    for (int j = tid; j < ES_TAB_N; j += ES_THREADS) {
+        const double v = exp2((double)j / ES_TAB_N);
+#pragma unroll
+        for (int r = 0; r < ES_TAB_REPL; ++r) etab[j * ES_TAB_REPL + r] = v;
+    }
     for (int e = tid; e < 8 * Z; e += ES_THREADS) coef[e] = a.st.coef[(size_t)b * 8 * Z + e];
     for (int e = tid; e < Z; e += ES_THREADS) logU[e] = a.st.logU[(size_t)b * Z + e];
     for (int e = tid; e < I * Z; e += ES_THREADS) om[e] = a.st.omega[(size_t)b * I * Z + e];
     const double base = a.st.base[b];
+    const double* tab_lane = etab + (lane & (ES_TAB_REPL - 1));
     __syncthreads();
     for (int xi = 0; xi < ES_XPB; ++xi) {
         const int x = blockIdx.x * ES_XPB + xi;
@@ -172,38 +220,62 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
         const double v = a.vmix[x];
         const double c0 = a.c0[(size_t)b * a.M + x];
         const double s = sqrt(v + 1e-4) / v;               // chol(v + var_noise) / v   (acquisitions.py:27,33-34)
-        if (tid < Z) {
-            const double tr = s * s * (c0 * c0 * coef[0 * Z + tid] + c0 * coef[1 * Z + tid] + coef[2 * Z + tid]);
-            const double ds = (c0 * c0 * coef[3 * Z + tid] + c0 * coef[4 * Z + tid] + coef[5 * Z + tid]) / v;
-            det[tid] = ds + 0.5 * tr;
-            sdm[tid] = s * (c0 * coef[6 * Z + tid] + coef[7 * Z + tid]);
+        if (w == 0) {                                      // Z <= 64: two rows per lane; bounds of the columns' maxima
+            double smax = 0.0, dmax = -INFINITY, dabs = 0.0;
+            bool fin = true;
+            for (int q = lane; q < Z; q += 32) {
+                const double tr = s * s * (c0 * c0 * coef[0 * Z + q] + c0 * coef[1 * Z + q] + coef[2 * Z + q]);
+                const double ds = (c0 * c0 * coef[3 * Z + q] + c0 * coef[4 * Z + q] + coef[5 * Z + q]) / v;
+                const double dt = ds + 0.5 * tr;
+                const double sm = s * (c0 * coef[6 * Z + q] + coef[7 * Z + q]);
+                sd[q] = make_double2(sm, dt);
+                smax = fmax(smax, fabs(sm)); dmax = fmax(dmax, dt); dabs = fmax(dabs, fabs(dt));
+                fin = fin && fabs(sm) < 1e100 && fabs(dt) < 1e100;      // false for NaN / inf as well
+            }
+            smax = warp_max(smax); dmax = warp_max(dmax); dabs = warp_max(dabs);
+            const unsigned allfin = __ballot_sync(0xffffffffu, fin);
+            if (lane == 0) { red[8] = smax; red[9] = dmax; red[10] = (allfin == 0xffffffffu) ? 1.0 : 0.0; red[11] = dabs; }
         }
         __syncthreads();
-        // two (innovation p, column bb) pairs per thread and pass (they share the det / sdm broadcasts and give the
-        // exp chains a partner to overlap with): I * Z columns over the whole CTA
+        const double smax = red[8], dmax = red[9], dabs = red[11];
+        const bool fin = red[10] != 0.0;
         double acc = 0.0;
         const int ncol = I * Z;
-        for (int c = tid; c < ncol; c += 2 * ES_THREADS) {
-            const int c2 = c + ES_THREADS;
-            const bool two = c2 < ncol;
-            const double o1 = om[c], o2 = two ? om[c2] : 0.0;     // om[p * Z + bb]
-            double mx1 = -INFINITY, mx2 = -INFINITY;
-            for (int q = 0; q < Z; ++q) {
-                const double sq = sdm[q], dq = det[q];
-                mx1 = fmax(mx1, fma(sq, o1, dq));
-                mx2 = fmax(mx2, fma(sq, o2, dq));
+        for (int c = tid; c < ncol; c += ES_NC * ES_THREADS) {
+            double o[ES_NC], se[ES_NC], sw[ES_NC];
+            int qref[ES_NC];
+#pragma unroll
+            for (int k = 0; k < ES_NC; ++k) {
+                const int ck = c + k * ES_THREADS;
+                o[k] = (ck < ncol) ? om[ck] : 0.0;          // om[p * Z + bb]
+                // every t_a = det_a + sdm_a * o of the column is <= dmax + smax |o|: reference exponent of its sums
+                const double mb = fma(fabs(o[k]), smax, dmax);
+                qref[k] = (int)floor(fmin(fmax(mb, -1e6), 1e6) * 1.4426950408889634) + 2;
+                se[k] = 0.0; sw[k] = 0.0;
             }
-            double se1 = 0.0, sw1 = 0.0, se2 = 0.0, sw2 = 0.0;
             for (int q = 0; q < Z; ++q) {
-                const double sq = sdm[q], dq = det[q];
-                const double t1 = fma(sq, o1, dq), t2 = fma(sq, o2, dq);
-                const double e1 = exp_neg_fast(mx1 - t1, etab);   // t <= mx; non-finite t makes the sums NaN -> nan_flag
-                const double e2 = exp_neg_fast(mx2 - t2, etab);
-                se1 += e1; sw1 = fma(e1, t1, sw1);
-                se2 += e2; sw2 = fma(e2, t2, sw2);
+                const double2 sq = sd[q];
+#pragma unroll
+                for (int k = 0; k < ES_NC; ++k) {
+                    const double t = fma(sq.x, o[k], sq.y);
+                    const double e = es_exp_scaled(t, qref[k], tab_lane);
+                    se[k] += e; sw[k] = fma(e, t, sw[k]);
+                }
             }
-            acc += base - (sw1 / se1 - (mx1 + log(se1)) + logU[c % Z]);
-            if (two) acc += base - (sw2 / se2 - (mx2 + log(se2)) + logU[c2 % Z]);
+#pragma unroll
+            for (int k = 0; k < ES_NC; ++k) {
+                const int ck = c + k * ES_THREADS;
+                if (ck < ncol) {
+                    double h;           // sum_a softmax_a t_a - logsumexp_a t_a of the column
+                    // fast path: every |t_a| <= dabs + smax |o| small enough for the 32-bit n of es_exp_scaled, and the
+                    // sums inside the exponent window around the reference (bound - maximum < ~800 binades)
+                    if (fin && fma(fabs(o[k]), smax, dabs) < 9.0e5 && se[k] > 1e-240 && se[k] < 1e300)
+                        h = sw[k] / se[k] - fma((double)qref[k], 0.69314718055994530942, log(se[k]));
+                    else
+                        h = es_column_exact(o[k], sd, Z);
+                    acc += base - (h + logU[ck % Z]);
+                }
+            }
         }
         acc = warp_sum(acc);
         if (lane == 0) red[w] = acc;
@@ -218,7 +290,7 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
 }
 
 __host__ __device__ inline size_t es_entropy_smem_bytes(int Z, int I) {
-    return 8 * (size_t)(8 * Z + Z + I * Z + 2 * Z + 8 + EXP_TAB_N) + 64;
+    return 8 * (size_t)(ES_TAB_N * ES_TAB_REPL + 8 * Z + Z + ((I * Z + 1) & ~1) + 2 * Z + 16) + 64;
 }
 
 // grid (ceil(M / 128)): ig[x] = mean_b partial[x][b] in fixed order; NaN -> flag.

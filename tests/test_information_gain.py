@@ -145,3 +145,45 @@ def test_information_gain_full_size_matches_reference_emulated(sim_engine):
     from tests.cusim.build_sim import build_sim
     from fabolas_b200 import Engine
     _full_pipeline(sim_engine, lambda: Engine(device="cpu", lib_path=build_sim()))
+
+
+def _extreme_innovations(eng):
+    """Innovation vectors far outside N(0, 1): the column sums of the entropy kernel leave the exponent range its fast
+    path covers (reference exponent from a bound on the column maximum), and it must fall back to the exact maximum --
+    same value as the reference's algorithm (acq_oracle restates acquisitions.py:119-167); a non-finite innovation
+    must surface as the NaN flag (the reference raises ArithmeticError, acquisitions.py:160-164)."""
+    g = golden("acq_ref.npz")
+    D = g["Xtrain"].shape[1]
+    B, I, Z = g["Omega"].shape
+    eng.set_data(1, g["Xtrain"], g["y"], float(g["y"].mean()), D)
+    eng.fit(g["theta"], g["yerr2"])
+    mu, var, cov = eng.predict(g["reps"], want_cov=True)
+    p_min = (g["pmin_logP"], g["pmin_dMu"], g["pmin_dSg"], g["pmin_dMM"])
+    models = []
+    for b in range(B):
+        gp = go.GP(go.build_kernel(1, g["theta"][b], D), mean=float(g["y"].mean())); gp.compute(g["Xtrain"], np.sqrt(g["yerr2"][b]))
+        models.append(gp)
+    pmin = [tuple(p[b] for p in p_min) for b in range(B)]
+    for scale in (1.0, 40.0, 2.0e3, 1.0e5):
+        Om = g["Omega"] * scale
+        eng.es_setup(g["reps"], cov, p_min, g["U"], Om)
+        ig, flag = eng.information_gain(g["tests"])
+        ig = ig.cpu().numpy() if hasattr(ig, "cpu") else ig.numpy()
+        assert int(flag.max()) == 0
+        Ol = [[Om[b, p][:, None] for p in range(I)] for b in range(B)]
+        ref = np.array([ao.information_gain(t, models, pmin, list(g["reps"]), list(g["U"]), Ol, {"y": g["y"]}, n_innovations=I)
+                        for t in g["tests"]])
+        assert np.max(np.abs(ig - ref) / np.maximum(1.0, np.abs(ref))) < 1e-8, (scale, ig, ref)
+    Om = g["Omega"].copy(); Om[1, 2, 3] = np.inf
+    eng.es_setup(g["reps"], cov, p_min, g["U"], Om)
+    ig, flag = eng.information_gain(g["tests"])
+    assert int(flag.min()) == 1 and bool(np.all(np.isnan(ig.cpu().numpy())))
+
+
+def test_information_gain_extreme_innovations_emulated(sim_engine):
+    _extreme_innovations(sim_engine)
+
+
+@pytest.mark.gpu
+def test_information_gain_extreme_innovations_gpu(gpu_engine):
+    _extreme_innovations(gpu_engine)
