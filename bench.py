@@ -49,7 +49,7 @@ ES_TRAFFIC_BYTES_PER_LAUNCH = None      # es_entropy_kernel; filled from the com
 ES_TRAFFIC_SOURCE = None
 # FP64-pipe instructions of es_entropy_kernel per (candidate, model, innovation, column, row) element -- counted in
 # the source and checked against the SASS of the inner loops
-ES_FP64_INSTR_PER_ELEMENT = 17
+ES_FP64_INSTR_PER_ELEMENT = 11
 
 
 def bench_config(n_gpus: int) -> dict:

@@ -17,7 +17,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "_lib", "libfabolas_b200.so")
+# FABOLAS_B200_LIB: development override (tools/ build kernel variants next to the shipped library and time them)
+DEFAULT_LIB = os.environ.get("FABOLAS_B200_LIB") or os.path.join(_HERE, "_lib", "libfabolas_b200.so")
 
 FAB_FAMILY_M52 = 0
 FAB_FAMILY_M52_BASIS = 1

@@ -19,7 +19,13 @@
 
 namespace fab {
 
-constexpr int ES_THREADS = 128;
+#ifndef FAB_ES_THREADS
+#define FAB_ES_THREADS 128
+#endif
+#ifndef FAB_ES_NC
+#define FAB_ES_NC 4
+#endif
+constexpr int ES_THREADS = FAB_ES_THREADS;
 constexpr int ES_XPB = 8;           // candidates per CTA in the entropy kernel
 
 struct EsState {
@@ -152,28 +158,44 @@ struct EsEntropyArgs {
 //   n = round(t * 256 / ln2) = 256 q + j ;  e^t = 2^q * 2^(j/256) * e^rr ,  rr = t - n ln2/256 , |rr| <= ln2/512
 //   2^(j/256) from a 256-entry table, e^rr by a degree-4 Taylor polynomial (remainder 3.8e-17), and the power of two
 //   2^(q - qref) added straight into the exponent field -- the reference shift of the log-sum-exp costs no FP64
-//   instruction.  11 FP64-pipe instructions per element with the two accumulations (t itself is the twelfth).
+//   instruction.  11 FP64-pipe instructions per element: t, T, nd, rr, four of the polynomial, table * p, and the two
+//   accumulations (17 with the former max pass + exp(t - max), profiles/r02a_es_entropy_before_rewrite_ncu_raw.csv).
 // The table is replicated over the 16 bank pairs of shared memory (entry j of lane l at tab[16 j + (l & 15)]): lanes
 // pick arbitrary entries, and without the replication the look-ups serialise ~5-fold on bank conflicts.
 constexpr int ES_TAB_N = 256;
-constexpr int ES_TAB_REPL = 16;
-constexpr int ES_NC = 4;            // columns per thread and pass: independent chains, broadcasts of det / sdm amortised
-__device__ __forceinline__ double es_exp_scaled(double t, int qref, const double* __restrict__ tab_lane) {
+#ifndef FAB_ES_REPL
+#define FAB_ES_REPL 16
+#endif
+#ifndef FAB_ES_UNROLL
+#define FAB_ES_UNROLL 4
+#endif
+#ifndef FAB_ES_MINB
+#define FAB_ES_MINB 1
+#endif
+constexpr int ES_TAB_REPL = FAB_ES_REPL;
+constexpr int ES_UNROLL = FAB_ES_UNROLL;    // rows of the innermost loop unrolled
+constexpr int ES_NC = FAB_ES_NC;    // columns per thread and pass: independent chains, broadcasts of det / sdm amortised
+__device__ __forceinline__ double es_exp_scaled(double t, int qref, const unsigned char* __restrict__ tab_lane) {
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
     const double T = fma(t, 369.32993046757462, MAGIC);      // 256 / ln2
     const double nd = T - MAGIC;
-    const int n = (int)(__double_as_longlong(T) & 0xffffffffLL);
-    double rr = fma(nd, -2.70760617331688990816e-03, t);     // ln2_hi / 256 (32 significant bits: nd * hi exact)
-    rr = fma(nd, -7.45396456746323320320e-13, rr);           // ln2_lo / 256
+    const int n = __double2loint(T);
+    // one FMA with the full-precision constant: |error| <= 3e-19 |nd| = 1.1e-16 |t|, the size of the rounding error t
+    // itself carries (in this kernel and in the reference's q = logP + det + sto alike); the exact two-constant
+    // reduction costs a twelfth FP64 instruction per element and 4.5 % of the kernel (profiles/r02e_es_variants.txt)
+    const double rr = fma(nd, -2.7076061740622863e-03, t);   // ln2 / 256
     double p = 4.1666666666666664e-02;                       // 1/4!
     p = fma(p, rr, 1.6666666666666666e-01);
     p = fma(p, rr, 0.5);
     p = fma(p, rr, 1.0);
     p = fma(p, rr, 1.0);
-    const double v = tab_lane[(n & (ES_TAB_N - 1)) * ES_TAB_REPL] * p;
-    const int dq = (n >> 8) - qref;                          // <= 0 by the choice of qref; < -1000: below 2^-1000 of the reference
-    const double w = __longlong_as_double(__double_as_longlong(v) + ((long long)dq << 52));
-    return (dq >= -1000) ? w : 0.0;
+    // entry (n & 255) of this lane's copy: byte offset (n & 255) * 128 from tab_lane
+    const double v = *reinterpret_cast<const double*>(tab_lane + ((unsigned)(n & (ES_TAB_N - 1)) * (ES_TAB_REPL * 8))) * p;
+    // 2^(q - qref) goes straight into the exponent field (high word).  q - qref <= 0 by the choice of qref; anything
+    // below 2^-1020 of the reference is pinned there instead of being flushed: the fast path is only taken when the
+    // sum is above 1e-240, so that such terms stay below 2^-200 of it.
+    const int dq = max((n >> 8) - qref, -1020);
+    return __hiloint2double(__double2hiint(v) + (dq << 20), __double2loint(v));
 }
 
 // One column the careful way (exact maximum first, polynomial exp without tables): the path of columns whose sums
@@ -193,7 +215,7 @@ __device__ __noinline__ double es_column_exact(double o, const double2* __restri
 
 // grid (ceil(M / ES_XPB), B): one model, ES_XPB candidates per CTA; the I * Z columns (innovation p, column bb) of a
 // candidate are dealt to the threads, ES_NC per thread and pass.
-__global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a) {
+__global__ void __launch_bounds__(ES_THREADS, FAB_ES_MINB) es_entropy_kernel(EsEntropyArgs a) {
     FAB_DYN_SMEM(smem_raw);
     const int Z = a.st.Z, I = a.st.I, b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = ES_THREADS / 32;
@@ -209,10 +231,11 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
         for (int r = 0; r < ES_TAB_REPL; ++r) etab[j * ES_TAB_REPL + r] = v;
     }
     for (int e = tid; e < 8 * Z; e += ES_THREADS) coef[e] = a.st.coef[(size_t)b * 8 * Z + e];
-    for (int e = tid; e < Z; e += ES_THREADS) logU[e] = a.st.logU[(size_t)b * Z + e];
     for (int e = tid; e < I * Z; e += ES_THREADS) om[e] = a.st.omega[(size_t)b * I * Z + e];
     const double base = a.st.base[b];
-    const double* tab_lane = etab + (lane & (ES_TAB_REPL - 1));
+    double logU_sum = 0.0;
+    for (int e = 0; e < Z; ++e) logU_sum += a.st.logU[(size_t)b * Z + e];
+    const unsigned char* tab_lane = reinterpret_cast<const unsigned char*>(etab + (lane & (ES_TAB_REPL - 1)));
     __syncthreads();
     for (int xi = 0; xi < ES_XPB; ++xi) {
         const int x = blockIdx.x * ES_XPB + xi;
@@ -253,6 +276,7 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
                 qref[k] = (int)floor(fmin(fmax(mb, -1e6), 1e6) * 1.4426950408889634) + 2;
                 se[k] = 0.0; sw[k] = 0.0;
             }
+#pragma unroll ES_UNROLL
             for (int q = 0; q < Z; ++q) {
                 const double2 sq = sd[q];
 #pragma unroll
@@ -273,7 +297,7 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
                         h = sw[k] / se[k] - fma((double)qref[k], 0.69314718055994530942, log(se[k]));
                     else
                         h = es_column_exact(o[k], sd, Z);
-                    acc += base - (h + logU[ck % Z]);
+                    acc -= h;
                 }
             }
         }
@@ -281,9 +305,11 @@ __global__ void __launch_bounds__(ES_THREADS) es_entropy_kernel(EsEntropyArgs a)
         if (lane == 0) red[w] = acc;
         __syncthreads();
         if (tid == 0) {
+            // dH of column (p, bb) = base - (h + logU[bb]); every bb occurs once per innovation: the logU terms and the
+            // base sum up to constants of the model (acquisitions.py:155-158)
             double t = 0.0;
             for (int q = 0; q < nw; ++q) t += red[q];
-            a.partial[(size_t)x * a.B + b] = t / ((double)Z * I);
+            a.partial[(size_t)x * a.B + b] = (t + (double)ncol * base - (double)I * logU_sum) / ((double)Z * I);
         }
         __syncthreads();
     }

@@ -229,6 +229,9 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+static inline int __double2loint(double d) { return (int)(unsigned)(__double_as_longlong(d) & 0xffffffffLL); }
+static inline int __double2hiint(double d) { return (int)(__double_as_longlong(d) >> 32); }
+static inline double __hiloint2double(int hi, int lo) { return __longlong_as_double(((long long)hi << 32) | (unsigned)lo); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
