@@ -46,6 +46,7 @@ SIGNATURES = {
     "fab_es_setup": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int]),
     "fab_es_information_gain_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
+    "fab_gp_prior_draw_batch": (_c_int, [_vp, _vp, _c_int, ctypes.c_ulonglong, _vp, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
     "fab_peer_alloc": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp]),
     "fab_peer_connect": (_c_int, [_vp, _vp]),
@@ -253,6 +254,20 @@ class Engine:
         if want_cov:
             out.append(cov)
         return tuple(out)
+
+    def prior_draw_max(self, reps, seed: int, want_sample: bool = False):
+        """max over the points of ONE prior draw GP.sample(reps[b]) per resident model (fabolas.py:198-199):
+        reps (B, Z, D) -> y_max (B,) [, sample (B, Z)], info (B,)."""
+        reps = self.tensor(reps)
+        if reps.dim() != 3 or reps.shape[0] != self.B or reps.shape[2] != self.D:
+            raise ValueError(f"reps must be ({self.B}, Z, {self.D})")
+        Z = reps.shape[1]
+        out = self.empty(self.B)
+        sample = self.empty(self.B, Z) if want_sample else None
+        info = self.empty(self.B, dtype=torch.int32)
+        self._check(self.lib.fab_gp_prior_draw_batch(self._ctx, _ptr(reps), Z, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out),
+                                                     _ptr(sample), _ptr(info)), "fab_gp_prior_draw_batch")
+        return (out, sample, info) if want_sample else (out, info)
 
     def expected_improvement(self, mu, var, y_max, xi: float = 0.0, want_ei: bool = True):
         """EI (B, M), best value (B,), argmax (B,) for predictive moments mu/var (B, M)."""

@@ -168,13 +168,15 @@ int fab_ctx_create(fab_ctx** out, int device, void* cuda_stream) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess && v > 0)
         c->smem_optin = v;
-    cudaFuncSetAttribute(gp_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    for (int d = 1; d <= MAX_D; ++d)
+        FAB_DISPATCH_D(d, cudaFuncSetAttribute(gp_dag_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+                          cudaFuncSetAttribute(mcmc_stretch_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               c->smem_optin - MCMC_STATIC_SMEM));
     cudaFuncSetAttribute(gp_predict_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(epmgp_ep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(epmgp_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(es_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ES_ENTROPY_SMEM_OPTIN);
     cudaFuncSetAttribute(gp_predict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-    cudaFuncSetAttribute(mcmc_stretch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - MCMC_STATIC_SMEM);
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->num_sms = v;
 #endif
     *out = c;
@@ -354,7 +356,7 @@ static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int 
         a.peer.world = p.world; a.peer.rank = p.rank; a.peer.rows_per_rank = p.rows_per_rank; a.peer.row_doubles = p.row_doubles;
     }
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
-    FAB_LAUNCH(gp_dag_kernel, B, DAG_THREADS, smem, c->stream, a);
+    FAB_DISPATCH_D(c->gd.d, FAB_LAUNCH(gp_dag_kernel<DD>, B, DAG_THREADS, smem, c->stream, a));
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }
     return FAB_OK;
@@ -557,6 +559,20 @@ int fab_kernel_matrix(fab_ctx* c, int family, int nu_code, const double* theta, 
     return FAB_OK;
 }
 
+int fab_gp_prior_draw_batch(fab_ctx* c, const double* reps, int Z, unsigned long long seed, double* out_max, double* sample,
+                            int* info) {
+    if (!c) return FAB_EINVAL;
+    if (!c->resident) return fail(c, FAB_ESTATE, "fab_gp_fit_batch has not been called");
+    if (!reps || !out_max) return fail(c, FAB_EINVAL, "null pointer");
+    if (Z < 1 || Z > 64) return fail(c, FAB_EUNSUPPORTED, "prior draws are limited to 1 <= Z <= 64 points per model");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    PriorDrawArgs a;
+    a.gd = c->gd; a.theta = c->dTheta; a.reps = reps; a.Z = Z; a.seed = seed; a.out_max = out_max; a.sample = sample; a.info = info;
+    FAB_LAUNCH(prior_draw_kernel, c->wsB, 128, 0, c->stream, a);
+    FAB_CUDA(c, cudaGetLastError());
+    return FAB_OK;
+}
+
 int fab_ei_batch(fab_ctx* c, const double* mu, const double* var, int B, int M, const double* y_max, double xi,
                  double* ei, double* best_val, long long* best_idx) {
     if (!c) return FAB_EINVAL;
@@ -736,11 +752,12 @@ static int mcmc_launch(fab_ctx* c, int prior, double* coords, double* log_prob, 
     }
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
 #ifdef FAB_CUSIM
-    FAB_LAUNCH(mcmc_stretch_kernel, grid, DAG_THREADS, smem, c->stream, m);
+    FAB_DISPATCH_D(gd.d, FAB_LAUNCH(mcmc_stretch_kernel<DD>, grid, DAG_THREADS, smem, c->stream, m));
 #else
     void* params[] = {&m};
-    FAB_CUDA(c, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mcmc_stretch_kernel), dim3(grid), dim3(DAG_THREADS),
-                                            params, smem, c->stream));
+    void* kern = nullptr;
+    FAB_DISPATCH_D(gd.d, kern = reinterpret_cast<void*>(mcmc_stretch_kernel<DD>));
+    FAB_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DAG_THREADS), params, smem, c->stream));
 #endif
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }

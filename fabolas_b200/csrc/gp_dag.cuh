@@ -99,7 +99,7 @@ __device__ __forceinline__ void build_acc(double (&acc)[4][2][2], const double* 
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const bool basis = family == 1;
     const double cb = basis ? h.cb : 1.0;
-#pragma unroll 1
+#pragma unroll 1      // two or four passes in flight measured no faster (259 / 260 us against 256), with spills
     for (int q = 0; q < 4; ++q) {
         const int ip = q >> 1, j = q & 1;
         const int lj0 = wt.n0 + 8 * j + 2 * t;
@@ -240,11 +240,13 @@ __device__ __forceinline__ void contract_acc(const double (&acc)[4][2][2], doubl
 // other (the device-resident ensemble sampler, mcmc.cuh): `first` marks the CTA's first one (exp table and
 // mbarriers are set up once), `phases` carries the mbarrier parities of the bulk warps across evaluations, and
 // the caller separates two evaluations by a __syncthreads().
+template <int DD>
 __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned char* smem_raw, unsigned& phases,
                                          const bool first) {
     const GpData& gd = a.gd;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int Np = gd.Np, N = gd.N, d = gd.d, Pk = gd.Pk;
+    const int Np = gd.Np, N = gd.N, Pk = gd.Pk;
+    constexpr int d = DD;                 // == gd.d (the host dispatches on it)
     const int SL = slice_doubles(d);
 
     double* slots = reinterpret_cast<double*>(smem_raw);
@@ -475,12 +477,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         if (flags & DOPF_GET_BEFORE) acc_load(acc, C, wt);      // partial tile P(I,J) continues in the accumulators
         switch (type) {
         case DOP_BUILD: {
-#define FAB_BUILD_ACC(DD) case DD: build_acc<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab); break;
-            switch (d) {
-                FAB_BUILD_ACC(1) FAB_BUILD_ACC(2) FAB_BUILD_ACC(3) FAB_BUILD_ACC(4)
-                FAB_BUILD_ACC(5) FAB_BUILD_ACC(6) FAB_BUILD_ACC(7) FAB_BUILD_ACC(8)
-            }
-#undef FAB_BUILD_ACC
+            build_acc<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab);
             break;
         }
         case DOP_MMA_NT:
@@ -561,12 +558,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
                 PHB(50);
                 const double* ar_p = a.resident ? alv + TS * I : al_r;
                 const double* ac_p = a.resident ? alv + TS * J : al_c;
-#define FAB_CONTRACT_CASE(DD) case DD: contract_acc<DD>(acc, gsum_w, zr_p, zc_p, ur_p, uc_p, ar_p, ac_p, ldz, h, N, gd.family, I, J, wt, etab); break;
-                switch (d) {
-                    FAB_CONTRACT_CASE(1) FAB_CONTRACT_CASE(2) FAB_CONTRACT_CASE(3) FAB_CONTRACT_CASE(4)
-                    FAB_CONTRACT_CASE(5) FAB_CONTRACT_CASE(6) FAB_CONTRACT_CASE(7) FAB_CONTRACT_CASE(8)
-                }
-#undef FAB_CONTRACT_CASE
+                contract_acc<DD>(acc, gsum_w, zr_p, zc_p, ur_p, uc_p, ar_p, ac_p, ldz, h, N, gd.family, I, J, wt, etab);
                 PHE(50);
             }
             break;
@@ -656,10 +648,27 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
 
 // 12 warps: 65536 / 384 = 170 -> 168 registers per thread.
 #define FAB_DAG_KERNEL_ATTR __global__ void __launch_bounds__(DAG_THREADS, 1)
+// One instantiation per number of Matern axes d = gd.d (1..MAX_D): the covariance generation and the contraction are
+// unrolled over d, and a kernel that carried all eight versions was 406 KB of code (the sampler 921 KB) -- far more
+// than the instruction caches hold, for straight-line tile code that runs once per op (profiles/r02g_*).
+template <int DD>
 FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     FAB_DYN_SMEM(smem_raw);
     unsigned phases = 0u;                 // mbarrier phase parity per slot (uniform over the bulk warps)
-    dag_eval(a, blockIdx.x, smem_raw, phases, true);
+    dag_eval<DD>(a, blockIdx.x, smem_raw, phases, true);
 }
+
+// host side: run `...` with `constexpr int DD = d`
+#define FAB_DISPATCH_D(d, ...)                                   \
+    switch (d) {                                                 \
+    case 1: { constexpr int DD = 1; __VA_ARGS__; } break;        \
+    case 2: { constexpr int DD = 2; __VA_ARGS__; } break;        \
+    case 3: { constexpr int DD = 3; __VA_ARGS__; } break;        \
+    case 4: { constexpr int DD = 4; __VA_ARGS__; } break;        \
+    case 5: { constexpr int DD = 5; __VA_ARGS__; } break;        \
+    case 6: { constexpr int DD = 6; __VA_ARGS__; } break;        \
+    case 7: { constexpr int DD = 7; __VA_ARGS__; } break;        \
+    default: { constexpr int DD = 8; __VA_ARGS__; } break;       \
+    }
 
 }  // namespace fab

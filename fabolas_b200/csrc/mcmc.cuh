@@ -191,6 +191,7 @@ __device__ __forceinline__ void box_barrier(const McmcArgs& m, unsigned& gen, un
 
 // Evaluate the log-probability of the P-vector in m.q (this CTA's record): thread 0 decodes the prior, the whole
 // CTA runs the likelihood.  Result valid in thread 0.
+template <int DD>
 __device__ __forceinline__ double mcmc_log_prob(const McmcArgs& m, unsigned char* smem_raw, unsigned& phases, bool& first,
                                                 int* flag) {
     const int cta = blockIdx.x;
@@ -204,7 +205,7 @@ __device__ __forceinline__ double mcmc_log_prob(const McmcArgs& m, unsigned char
     __syncthreads();
     const bool run = *flag != 0;                  // uniform over the CTA
     if (run) {
-        dag_eval(m.dag, cta, smem_raw, phases, first);
+        dag_eval<DD>(m.dag, cta, smem_raw, phases, first);
         first = false;
     }
     __syncthreads();
@@ -216,6 +217,7 @@ __device__ __forceinline__ double mcmc_log_prob(const McmcArgs& m, unsigned char
     return 0.0;
 }
 
+template <int DD>
 __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m) {
     FAB_DYN_SMEM(smem_raw);
     __shared__ int flag[4];
@@ -232,86 +234,84 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
     // every rank's kernel is running: whatever its stream did before (initial state, copies of the last chain) is done
     if (m.world > 1) box_barrier(m, gen, xgen);
 
-    if (m.init_lp) {                              // emcee: state.log_prob = compute_log_prob(coords) when not given
-        for (int i = cta * W + R; i < K; i += gridDim.x * W) {
-            if (tid < P) q[tid] = ld_cg(&m.coords[(size_t)i * P + tid]);
+    // One loop over "rounds" so that the evaluation (the bulk of the code) is instantiated ONCE: round -1 computes the
+    // log-probability of the initial positions (emcee: state.log_prob = compute_log_prob(coords) when not given),
+    // rounds 2 * step + split are the half-steps.
+    for (int round = m.init_lp ? -1 : 0; round < 2 * m.nsteps; ++round) {
+        const bool init = round < 0;
+        const int step = init ? 0 : round >> 1, split = init ? 0 : round & 1;
+        const long long iter = m.iter0 + step;
+        if (!init && split == 0) {
+            // ---- split of this step: rank the K keys; order[r] = walker of rank r ----
+            for (int i = tid; i < K; i += DAG_THREADS)
+                keys[i] = ((unsigned long long)mcmc_rand(m.seed, iter, 0, i).x << 32) | (unsigned)i;
             __syncthreads();
-            const double v = mcmc_log_prob(m, smem_raw, phases, first, flag);
-            if (tid == 0) {
-                if (m.world > 1) { for (int r = 0; r < W; ++r) m.peer_lp[r][i] = v; }
-                else m.lp[i] = v;
+            for (int i = tid; i < K; i += DAG_THREADS) {
+                const unsigned long long ki = keys[i];
+                int r = 0;
+                for (int j = 0; j < K; ++j) r += keys[j] < ki;
+                order[r] = i;
+            }
+            __syncthreads();
+        }
+        const int items = init ? K : half;
+        for (int mm = cta * W + R; mm < items; mm += gridDim.x * W) {
+            const int s = init ? mm : order[split * half + mm];
+            double zfac = 0.0;
+            if (init) {
+                if (tid < P) q[tid] = ld_cg(&m.coords[(size_t)s * P + tid]);
+            } else if (tid == 0) {
+                const Philox4 r = mcmc_rand(m.seed, iter, 1 + split, mm);
+                const double u = uniform53(r.x, r.y);
+                const double zz = ((m.a - 1.0) * u + 1.0) * ((m.a - 1.0) * u + 1.0) / m.a;
+                int rint = (int)(((unsigned long long)r.z * (unsigned)half) >> 32);
+                const int c = order[(1 - split) * half + rint];
+                for (int k = 0; k < P; ++k) {
+                    const double ck = ld_cg(&m.coords[(size_t)c * P + k]);
+                    const double sk = ld_cg(&m.coords[(size_t)s * P + k]);
+                    q[k] = ck - (ck - sk) * zz;
+                }
+                zfac = (P - 1.0) * log(zz);
+            }
+            __syncthreads();
+            const double new_lp = mcmc_log_prob<DD>(m, smem_raw, phases, first, flag);
+            if (tid == 0 && init) {
+                if (m.world > 1) { for (int r = 0; r < W; ++r) m.peer_lp[r][s] = new_lp; }
+                else m.lp[s] = new_lp;
+            } else if (tid == 0) {
+                const double old_lp = ld_cg(&m.lp[s]);
+                const double lnpdiff = zfac + new_lp - old_lp;          // NaN (-inf - -inf) compares false: rejected
+                const Philox4 r = mcmc_rand(m.seed, iter, 3 + split, mm);
+                const bool acc = lnpdiff > log(uniform53(r.x, r.y));
+                if (acc) {
+                    if (m.world > 1) {                                  // every replica, this rank's included
+                        for (int r = 0; r < W; ++r) {
+                            for (int k = 0; k < P; ++k) m.peer_coords[r][(size_t)s * P + k] = q[k];
+                            m.peer_lp[r][s] = new_lp;
+                        }
+                    } else {
+                        for (int k = 0; k < P; ++k) m.coords[(size_t)s * P + k] = q[k];
+                        m.lp[s] = new_lp;
+                    }
+                    if (m.nacc) m.nacc[s] += 1;                         // counted on the owning rank
+                }
+                if (split == 1 && (m.chain || m.chain_lp)) {
+                    // after the second half-step: record this walker and the first-half walker of the same rank
+                    const int s0 = order[mm];
+                    const size_t row = (size_t)step * K;
+                    if (m.chain)
+                        for (int k = 0; k < P; ++k) {
+                            m.chain[(row + s) * P + k] = acc ? q[k] : ld_cg(&m.coords[(size_t)s * P + k]);
+                            m.chain[(row + s0) * P + k] = ld_cg(&m.coords[(size_t)s0 * P + k]);
+                        }
+                    if (m.chain_lp) {
+                        m.chain_lp[row + s] = acc ? new_lp : old_lp;
+                        m.chain_lp[row + s0] = ld_cg(&m.lp[s0]);
+                    }
+                }
             }
         }
         box_barrier(m, gen, xgen);
-    }
-
-    for (int step = 0; step < m.nsteps; ++step) {
-        const long long iter = m.iter0 + step;
-        // ---- split of this step: rank the K keys; order[r] = walker of rank r ----
-        for (int i = tid; i < K; i += DAG_THREADS)
-            keys[i] = ((unsigned long long)mcmc_rand(m.seed, iter, 0, i).x << 32) | (unsigned)i;
-        __syncthreads();
-        for (int i = tid; i < K; i += DAG_THREADS) {
-            const unsigned long long ki = keys[i];
-            int r = 0;
-            for (int j = 0; j < K; ++j) r += keys[j] < ki;
-            order[r] = i;
-        }
-        __syncthreads();
-        for (int split = 0; split < 2; ++split) {
-            for (int mm = cta * W + R; mm < half; mm += gridDim.x * W) {
-                const int s = order[split * half + mm];
-                double zfac = 0.0;
-                if (tid == 0) {
-                    const Philox4 r = mcmc_rand(m.seed, iter, 1 + split, mm);
-                    const double u = uniform53(r.x, r.y);
-                    const double zz = ((m.a - 1.0) * u + 1.0) * ((m.a - 1.0) * u + 1.0) / m.a;
-                    int rint = (int)(((unsigned long long)r.z * (unsigned)half) >> 32);
-                    const int c = order[(1 - split) * half + rint];
-                    for (int k = 0; k < P; ++k) {
-                        const double ck = ld_cg(&m.coords[(size_t)c * P + k]);
-                        const double sk = ld_cg(&m.coords[(size_t)s * P + k]);
-                        q[k] = ck - (ck - sk) * zz;
-                    }
-                    zfac = (P - 1.0) * log(zz);
-                }
-                __syncthreads();
-                const double new_lp = mcmc_log_prob(m, smem_raw, phases, first, flag);
-                if (tid == 0) {
-                    const double old_lp = ld_cg(&m.lp[s]);
-                    const double lnpdiff = zfac + new_lp - old_lp;          // NaN (-inf - -inf) compares false: rejected
-                    const Philox4 r = mcmc_rand(m.seed, iter, 3 + split, mm);
-                    const bool acc = lnpdiff > log(uniform53(r.x, r.y));
-                    if (acc) {
-                        if (m.world > 1) {                                  // every replica, this rank's included
-                            for (int r = 0; r < W; ++r) {
-                                for (int k = 0; k < P; ++k) m.peer_coords[r][(size_t)s * P + k] = q[k];
-                                m.peer_lp[r][s] = new_lp;
-                            }
-                        } else {
-                            for (int k = 0; k < P; ++k) m.coords[(size_t)s * P + k] = q[k];
-                            m.lp[s] = new_lp;
-                        }
-                        if (m.nacc) m.nacc[s] += 1;                         // counted on the owning rank
-                    }
-                    if (split == 1 && (m.chain || m.chain_lp)) {
-                        // after the second half-step: record this walker and the first-half walker of the same rank
-                        const int s0 = order[mm];
-                        const size_t row = (size_t)step * K;
-                        if (m.chain)
-                            for (int k = 0; k < P; ++k) {
-                                m.chain[(row + s) * P + k] = acc ? q[k] : ld_cg(&m.coords[(size_t)s * P + k]);
-                                m.chain[(row + s0) * P + k] = ld_cg(&m.coords[(size_t)s0 * P + k]);
-                            }
-                        if (m.chain_lp) {
-                            m.chain_lp[row + s] = acc ? new_lp : old_lp;
-                            m.chain_lp[row + s0] = ld_cg(&m.lp[s0]);
-                        }
-                    }
-                }
-            }
-            box_barrier(m, gen, xgen);
-        }
     }
 }
 

@@ -69,11 +69,7 @@ def entropy_search(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_inno
     K = len(models)
     reps = np.random.uniform(low=[b[0] for b in bounds], high=[b[1] for b in bounds], size=(K, n_gen_samples, D))
     mean, _, cov = eng.predict(reps, want_var=True, want_cov=True)
-    y_max = np.empty(K)
-    for k in range(K):
-        Kk = eng.kernel_matrix(FAB_FAMILY_M52, theta[k], reps[k], amp_mult=D)[0].cpu().numpy()
-        Kk[np.diag_indices_from(Kk)] += 1.25e-12
-        y_max[k] = np.random.multivariate_normal(np.full(n_gen_samples, models.mean), Kk).max()   # Q5
+    y_max, _ = eng.prior_draw_max(reps, seed=int(np.random.randint(0, 2 ** 31 - 1)))     # Q5: regressor.sample(reps).max()
     U, _, _ = eng.expected_improvement(mean, torch.diagonal(cov, dim1=1, dim2=2).contiguous(), y_max)
     p_min = epmgp.joint_min_batch(mean, cov, with_derivatives=True, engine=eng)
     Omega = np.random.normal(size=(K, n_innovations, n_gen_samples))

@@ -116,12 +116,9 @@ def prepare_candidate_search(dataset, bounds, n_hyper_samples=20, n_gen_samples=
     mean, _, cov = eng.predict(reps, want_var=True, want_cov=True)
     eps = np.finfo(np.float64).eps
     cov_clip = torch.clamp(cov, min=eps)                                               # Q6
-    # incumbent of EI = max of a PRIOR draw at the representers (Q5)
-    y_max = np.empty(K)
-    for k in range(K):
-        Kk = eng.kernel_matrix(FAB_FAMILY_M52_BASIS, theta[k], reps[k], amp_mult=D)[0].cpu().numpy()
-        Kk[np.diag_indices_from(Kk)] += 1.25e-12
-        y_max[k] = np.random.multivariate_normal(np.full(n_gen_samples, models.mean), Kk).max()
+    # incumbent of EI = max of a PRIOR draw at the representers (Q5: regressor.sample(reps), fabolas.py:198-199), one
+    # launch for all K models; numpy's global state (which the reference draws from) picks the seed of the device stream
+    y_max, _ = eng.prior_draw_max(reps, seed=int(np.random.randint(0, 2 ** 31 - 1)))
     var_reps = torch.diagonal(cov_clip, dim1=1, dim2=2).contiguous()
     ei, _, _ = eng.expected_improvement(mean, var_reps, y_max)
     U = torch.clamp(ei, min=eps)

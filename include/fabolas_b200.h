@@ -91,6 +91,15 @@ int fab_gp_fit_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int
 int fab_gp_predict_batch(fab_ctx* ctx, const double* T, int per_model, int M, double* mu, double* var,
                          double* cov);
 
+/* GP.sample(t).max() of every resident model at its own points: the incumbent the reference hands to
+ * expected_improvement is the maximum of ONE draw from the PRIOR N(mean, k(t,t) + 1.25e-12 I) at the representer
+ * points (fabolas.py:198-199, entropy_search.py:137).  reps B x Z x D (Z <= 64); out_max B; sample B x Z or NULL (the
+ * draw itself); info B or NULL (pivots of the covariance that were not positive and were dropped, normally 0).
+ * The normals are Box-Muller pairs of the Philox4x32-10 stream keyed by (seed, model, pair): a pure function of the
+ * seed, reproducible on the host (tests/test_prior_draw.py); parity with numpy's generator is distributional.   */
+int fab_gp_prior_draw_batch(fab_ctx* ctx, const double* reps, int Z, unsigned long long seed, double* out_max,
+                            double* sample, int* info);
+
 /* acquisitions.expected_improvement (acquisitions.py:40-75) on B x M predictive moments, plus the
  * np.argmax of expected_improvement.get_candidate (expected_improvement.py:92-93) per model:
  * ei (B x M), best_val (B), best_idx (B, int64) may each be NULL.  y_max: B incumbents.           */

@@ -241,7 +241,9 @@ def _batched_fd_equals_plain(ds, bounds, **kw):
     pts = [x0] + [np.array([rng.uniform(lo + 0.05 * (hi - lo), hi - 0.05 * (hi - lo)) for lo, hi in bounds]) for _ in range(3)]
     for x in pts:
         v, g = fun(x)
-        assert v == plain(x)                                     # same kernels, same inputs: bit-identical value
+        # same kernels, same inputs; the mixture mean over the models is a torch reduction whose order depends on the
+        # batch shape, so the last bit may differ
+        assert abs(v - plain(x)) <= 4e-16 * abs(v)
         gref = approx_fprime(x, plain, 1e-8)
         assert np.allclose(g, gref, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(gref).max())), (g, gref)
     ra = minimize(fun=fun, x0=x0, jac=True, method="L-BFGS-B", bounds=bounds, options={"maxiter": 4})
