@@ -66,6 +66,7 @@ SIGNATURES = {
     "fab_ctx_debug_set_mcmc_ctas": (_c_int, [_vp, _c_int]),
     "fab_ctx_debug_set_max_slots": (_c_int, [_vp, _c_int]),
     "fab_ctx_debug_force_slices": (_c_int, [_vp, _c_int]),
+    "fab_ctx_debug_set_predict_chunk": (_c_int, [_vp, _c_int]),
     "fab_gp_debug_get_factor": (_c_int, [_vp, _c_int, _vp]),
     "fab_debug_dag_verify": (_c_int, [_c_int, _c_int, _c_int, ctypes.c_char_p, _c_int, ctypes.POINTER(_c_int)]),
 }
@@ -154,6 +155,9 @@ class Engine:
 
     def debug_set_max_slots(self, n: int):
         self._check(self.lib.fab_ctx_debug_set_max_slots(self._ctx, n), "fab_ctx_debug_set_max_slots")
+
+    def debug_set_predict_chunk(self, jc: int):
+        self._check(self.lib.fab_ctx_debug_set_predict_chunk(self._ctx, int(jc)), "fab_ctx_debug_set_predict_chunk")
 
     def debug_force_slices(self, on: bool):
         self._check(self.lib.fab_ctx_debug_force_slices(self._ctx, int(on)), "fab_ctx_debug_force_slices")

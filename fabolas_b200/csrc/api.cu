@@ -75,6 +75,8 @@ struct fab_ctx {
     size_t cap_mc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int num_sms = 148;
     double* eiVal = nullptr; long long* eiIdx = nullptr; size_t cap_ei[2] = {0, 0};   // per-chunk argmax partials
+    double* vpart = nullptr; size_t capVpart = 0;     // prediction with a chunked panel: partial rows of V per CTA
+    int predict_jc = 0;          // test knob: cap on the resident tile rows of the cross-covariance panel (0 = whatever fits)
     int mcmc_max_ctas = 0;       // test knob: cap the sampler's grid (0 = one CTA per proposal, up to the SM count)
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
@@ -198,7 +200,7 @@ int fab_ctx_destroy(fab_ctx* c) {
     cudaFree(c->wkSpill);
     peer_release(c);
     mpeer_release(c);
-    cudaFree(c->eiVal); cudaFree(c->eiIdx);
+    cudaFree(c->eiVal); cudaFree(c->eiIdx); cudaFree(c->vpart);
     cudaFree(c->mcTheta); cudaFree(c->mcYerr2); cudaFree(c->mcLl); cudaFree(c->mcQ); cudaFree(c->mcInfo);
     cudaFree(c->mcKeys); cudaFree(c->mcOrder); cudaFree(c->mcBar);
     cudaFree(c->wk.Lw); cudaFree(c->wk.zvec); cudaFree(c->wk.alpha); cudaFree(c->wk.accw);
@@ -223,6 +225,12 @@ int fab_debug_dag_verify(int NT, int nslot, int mode, char* msg, int msg_len, in
         stats[0] = (int)P.bulk.size(); stats[1] = (int)P.chain.size(); stats[2] = nl; stats[3] = ns;
     }
     return e.empty() ? 0 : -1;
+}
+
+int fab_ctx_debug_set_predict_chunk(fab_ctx* c, int jc) {
+    if (!c || jc < 0) return FAB_EINVAL;
+    c->predict_jc = jc;
+    return FAB_OK;
 }
 
 int fab_ctx_debug_force_slices(fab_ctx* c, int on) {
@@ -406,21 +414,42 @@ static int launch_predict(fab_ctx* c, const double* T, long long T_bstride, int 
     a.mu = mu; a.var = var; a.cov = cov; a.dotvec = dotvec; a.dot = dot; a.vcol = vcol; a.vcol_index = vcol_index;
     const bool want_cov = cov != nullptr;
     if (want_cov && M > 64) return fail(c, FAB_EUNSUPPORTED, "full predictive covariance is limited to M <= 64 points");
-    // widest candidate block that fits, with two W tile buffers when they fit as well
-    int CB = 0, nbuf = 0;
-    for (int cb : {64, 32}) {
-        if (cb == 32 && want_cov) break;
-        for (int nb : {2, 1})
-            if (!CB && predict_smem_bytes(cb, gd.NT, gd.Np, gd.d, want_cov, nb) <= (size_t)c->smem_optin) { CB = cb; nbuf = nb; }
-        if (CB) break;
+    // widest candidate block whose whole cross-covariance panel (N x CB) fits, with two W tile buffers when they fit as
+    // well; otherwise (N > 512) the panel is generated jc tile rows at a time and the rows of V that later chunks
+    // continue wait in a per-CTA scratch region -- any N
+    int CB = 0, nbuf = 0, jc = gd.NT;
+    const int jc_cap = c->predict_jc > 0 ? c->predict_jc : gd.NT;          // test knob
+    if (jc_cap >= gd.NT)
+        for (int cb : {64, 32}) {
+            if (cb == 32 && want_cov) break;
+            for (int nb : {2, 1})
+                if (!CB && predict_smem_bytes(cb, gd.NT, gd.d, want_cov, nb) <= (size_t)c->smem_optin) { CB = cb; nbuf = nb; }
+            if (CB) break;
+        }
+    if (!CB) {
+        CB = want_cov ? 64 : 32; nbuf = 2;
+        jc = jc_cap < gd.NT ? jc_cap : gd.NT;
+        while (jc > 1 && predict_smem_bytes(CB, jc, gd.d, want_cov, nbuf) > (size_t)c->smem_optin) --jc;
+        if (predict_smem_bytes(CB, jc, gd.d, want_cov, nbuf) > (size_t)c->smem_optin)
+            return fail(c, FAB_EUNSUPPORTED, "not enough shared memory for the prediction kernel");
     }
-    if (!CB) return fail(c, FAB_EUNSUPPORTED, "N too large for the single-CTA prediction kernel");
-    a.nbuf = nbuf;
-    const size_t smem = predict_smem_bytes(CB, gd.NT, gd.Np, gd.d, want_cov, nbuf);
+    a.nbuf = nbuf; a.jc = jc; a.B = c->wsB; a.vpart = nullptr;
+    const long long nblk = ((long long)M + CB - 1) / CB;
+    dim3 grid((unsigned)nblk, (unsigned)c->wsB);
+    if (jc < gd.NT) {                       // persistent grid: one scratch region per CTA
+        const long long items = nblk * c->wsB;
+        const long long cap = c->predict_jc > 0 ? 2 : c->num_sms;      // (test knob: two CTAs walk all the items)
+        const unsigned G = (unsigned)(items < cap ? items : cap);
+        grid = dim3(G, 1);
+        int rc = ensure(c, &c->vpart, &c->capVpart, (size_t)G * gd.NT * TS * CB);
+        if (rc != FAB_OK) return rc;
+        a.vpart = c->vpart;
+    }
+    const size_t smem = predict_smem_bytes(CB, jc, gd.d, want_cov, nbuf);
     if (CB == 64) {
-        FAB_LAUNCH(gp_predict_kernel<64>, dim3((M + 63) / 64, c->wsB), NTHREADS, smem, c->stream, a);
+        FAB_LAUNCH(gp_predict_kernel<64>, grid, NTHREADS, smem, c->stream, a);
     } else {
-        FAB_LAUNCH(gp_predict_kernel<32>, dim3((M + 31) / 32, c->wsB), NTHREADS, smem, c->stream, a);
+        FAB_LAUNCH(gp_predict_kernel<32>, grid, NTHREADS, smem, c->stream, a);
     }
     FAB_CUDA(c, cudaGetLastError());
     return FAB_OK;
@@ -431,7 +460,12 @@ int fab_gp_predict_batch(fab_ctx* c, const double* T, int per_model, int M, doub
     if (!c->resident) return fail(c, FAB_ESTATE, "fab_gp_fit_batch has not been called");
     if (!T || M < 1 || (!mu && !var && !cov)) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    return launch_predict(c, T, per_model ? (long long)M * c->gd.D : 0, M, mu, var, cov, nullptr, nullptr);
+    FAB_MARK(c, 0);
+    const int rc = launch_predict(c, T, per_model ? (long long)M * c->gd.D : 0, M, mu, var, cov, nullptr, nullptr);
+    if (rc != FAB_OK) return rc;
+    FAB_MARK(c, 1);
+    if (c->timing) c->ev_used = 1;
+    return FAB_OK;
 }
 
 int fab_epmgp_joint_min_batch(fab_ctx* c, const double* mu, const double* Sigma, int B, int Z, double* logP,

@@ -21,6 +21,7 @@ struct PredictArgs {
     const double* T;         // M x D candidates (last column = basis input as given by the caller)
     long long T_bstride;     // 0: all models share T ; M*D: model b reads T + b*T_bstride (per-model points)
     int M;
+    int B;                   // resident models
     double* mu;              // B x M or null
     double* var;             // B x M or null
     double* cov;             // B x M x M or null (M <= 64 only)
@@ -29,27 +30,31 @@ struct PredictArgs {
     double* vcol;            // B x Np or null: column `vcol_index` of V = W K*^T (first block only)
     int vcol_index;
     int nbuf;                // W tile buffers in shared memory: 2 (load of tile t+1 overlaps the product of tile t) or 1
+    int jc;                  // tile rows of the cross-covariance panel resident at a time (>= NT: the whole panel)
+    double* vpart;           // jc < NT: per-CTA scratch for the partial rows of V (grid x NT x 64 x CB doubles)
 };
 
-// Shared memory: the panel (NT x 64 x CB), then a region used twice -- first by the scaled observation
-// coordinates, the basis column and alpha while the panel is generated, then by the W tile buffers of the
+// Shared memory: the resident part of the panel (jc x 64 x CB), then a region used twice -- first by the scaled
+// observation coordinates, the basis column and alpha of the rows being generated, then by the W tile buffers of the
 // product loop --, the optional covariance scratch, the candidate coordinates, the exp table, partial sums.
-__host__ __device__ inline size_t predict_union_doubles(int Np, int d, int nbuf) {
-    const size_t coords = (size_t)(d + 2) * Np, wb = (size_t)nbuf * TILE_ELEMS;
+__host__ __device__ inline size_t predict_union_doubles(int rows, int d, int nbuf) {
+    const size_t coords = (size_t)(d + 2) * rows, wb = (size_t)nbuf * TILE_ELEMS;
     return coords > wb ? coords : wb;
 }
-__host__ __device__ inline size_t predict_smem_bytes(int CB, int NT, int Np, int d, bool cov, int nbuf) {
-    size_t doubles = (size_t)NT * TS * CB + predict_union_doubles(Np, d, nbuf) + (cov ? TS * CB : 0) +
+__host__ __device__ inline size_t predict_smem_bytes(int CB, int jc, int d, bool cov, int nbuf) {
+    size_t doubles = (size_t)jc * TS * CB + predict_union_doubles(jc * TS, d, nbuf) + (cov ? TS * CB : 0) +
                      (size_t)(d + 1) * CB + EXP_TAB_N + 3 * 8 * CB + 16;
     return doubles * 8 + 64;
 }
 
 // One 8-row strip of the cross-covariance panel per warp and pass: lane = candidate column, four rows in
 // flight (independent Matern chains), candidate coordinates in registers, observation coordinates broadcast.
+// Generates the `nt` tile rows whose observations are staged in zs / us / al (row stride `ld`); `row0` is the
+// global index of the first staged observation.  pmu accumulates the mean partials.
 template <int DD, int CB>
 __device__ __forceinline__ void predict_panel(double* Ks, const double* zs, const double* us, const double* al,
                                               const double* tz, const double* tu, const Hyper& h, int family, int N,
-                                              int Np, int NT, int ncand, const double* __restrict__ etab,
+                                              int ld, int nt, int row0, int ncand, const double* __restrict__ etab,
                                               double (&pmu)[CB / 32]) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool basis = family == 1;
@@ -63,214 +68,261 @@ __device__ __forceinline__ void predict_panel(double* Ks, const double* zs, cons
         const double cbv = basis ? h.cb : 1.0;
         const bool cok = c < ncand;
         double pm = 0.0;
-        for (int J = 0; J < NT; ++J) {
+        for (int J = 0; J < nt; ++J) {
             double* P = Ks + (size_t)J * TS * CB;
 #pragma unroll
             for (int r4 = 0; r4 < 2; ++r4) {
                 double v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int gi = TS * J + 8 * w + 4 * r4 + u;
+                    const int li = TS * J + 8 * w + 4 * r4 + u;
                     double r2 = 0.0;
 #pragma unroll
                     for (int k = 0; k < DD; ++k) {
-                        const double dz = zs[k * Np + gi] - tc[k];
+                        const double dz = zs[k * ld + li] - tc[k];
                         r2 = fma(dz, dz, r2);
                     }
-                    const double kv = h.amp * matern52_fast_value(r2, etab) * fma(us[gi], tuc, cbv);
-                    v[u] = (gi < N && cok) ? kv : 0.0;
-                    pm = fma(v[u], al[gi], pm);
+                    const double kv = h.amp * matern52_fast_value(r2, etab) * fma(us[li], tuc, cbv);
+                    v[u] = (row0 + li < N && cok) ? kv : 0.0;
+                    pm = fma(v[u], al[li], pm);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) P[tixw<CB>(8 * w + 4 * r4 + u, c)] = v[u];
             }
         }
-        pmu[q] = pm;
+        pmu[q] += pm;
     }
 }
 
+// Grid: every CTA takes the work items (candidate block, model) item = linear CTA index, + number of CTAs, ...
+// (the whole panel fits: one item per CTA, grid (blocks, B); panel in chunks: a persistent grid, one scratch region
+// for the partial rows of V per CTA).
 template <int CB>
 __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(PredictArgs a) {
     constexpr int MI = (CB == 64) ? 4 : 2;
     constexpr int NJ = 2;
     constexpr int NRG = (CB == 64) ? 2 : 4;        // warp row groups
+    constexpr int NACC = MI * NJ * 2;
     FAB_DYN_SMEM(smem_raw);
     const GpData& gd = a.gd;
-    const int b = blockIdx.y, blk = blockIdx.x;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int Np = gd.Np, NT = gd.NT, N = gd.N, d = gd.d, D = gd.D;
     const bool want_cov = a.cov != nullptr;
+    const int JC = a.jc < NT ? a.jc : NT;
+    const int rows_c = JC * TS;
 
-    double* Ks = reinterpret_cast<double*>(smem_raw);            // NT panels of 64 x CB
-    double* uni = Ks + (size_t)NT * TS * CB;                      // coordinates, then W tile buffers
+    double* Ks = reinterpret_cast<double*>(smem_raw);            // JC panels of 64 x CB
+    double* uni = Ks + (size_t)JC * TS * CB;                      // coordinates, then W tile buffers
     double* zs = uni;
-    double* us = zs + (size_t)d * Np;
-    double* al = us + Np;
+    double* us = zs + (size_t)d * rows_c;
+    double* al = us + rows_c;
     double* Wbuf = uni;
-    double* Vscr = uni + predict_union_doubles(Np, d, a.nbuf);
+    double* Vscr = uni + predict_union_doubles(rows_c, d, a.nbuf);
     double* tz = Vscr + (want_cov ? TS * CB : 0);                  // d x CB
     double* tu = tz + (size_t)d * CB;                              // CB
     double* etab = tu + CB;
     double* part = etab + EXP_TAB_N;                               // 3 x 8 x CB
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(part + 3 * 8 * CB);   // [2]
 
-    const Hyper h = decode_hyper(gd, a.theta + (size_t)b * gd.Pk, a.yerr2[b]);
-    const double* Lw = a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS;
-    const int c_base = blk * CB;
-
     exp_table_fill(etab);
-    for (int e = tid; e < N * D; e += NTHREADS) {
-        const int i = e / D, k = e - i * D;
-        const double x = __ldg(&gd.X[e]);
-        if (k < d) zs[k * Np + i] = x * h.scale[k];
-        if (gd.family == 1 && k == d) us[i] = x;
-    }
-    for (int i = tid; i < Np; i += NTHREADS) {
-        if (i >= N) {
-            for (int k = 0; k < d; ++k) zs[k * Np + i] = 0.0;
-            us[i] = 0.0;
-        }
-        if (gd.family != 1 && i < N) us[i] = 0.0;
-        al[i] = a.wk.alpha[(size_t)b * Np + i];
-    }
-    for (int e = tid; e < CB * D; e += NTHREADS) {
-        const int c = e / D, k = e - c * D;
-        const int gc = c_base + c;
-        const double x = (gc < a.M) ? __ldg(&a.T[(size_t)b * a.T_bstride + (size_t)gc * D + k]) : 0.0;
-        if (k < d) tz[k * CB + c] = x * h.scale[k];
-        if (k == d) tu[c] = x;
-    }
-    if (gd.family != 1) for (int c = tid; c < CB; c += NTHREADS) tu[c] = 0.0;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
-    __syncthreads();
-
-    // ---- cross-covariance panel K*^T (obs x cand) + mean partials ----
-    double pmu[CB / 32];
-#define FAB_PANEL_CASE(DD) case DD: predict_panel<DD, CB>(Ks, zs, us, al, tz, tu, h, gd.family, N, Np, NT, a.M - c_base, etab, pmu); break;
-    switch (d) {
-        FAB_PANEL_CASE(1) FAB_PANEL_CASE(2) FAB_PANEL_CASE(3) FAB_PANEL_CASE(4)
-        FAB_PANEL_CASE(5) FAB_PANEL_CASE(6) FAB_PANEL_CASE(7) FAB_PANEL_CASE(8)
-    }
-#undef FAB_PANEL_CASE
-#pragma unroll
-    for (int q = 0; q < CB / 32; ++q) part[w * CB + lane + 32 * q] = pmu[q];
-    fence_proxy_async();                   // the coordinate region is about to be overwritten by bulk copies
-    __syncthreads();
-
-    // ---- V = W K*^T, reduced on the fly; W tiles stream through `nbuf` buffers ----
+    unsigned waits[2] = {0u, 0u};          // completed waits per W buffer: the parity of the next one (uniform)
     const WarpTile wt = (CB == 64) ? warp_tile() : warp_tile_32();
-    double css[NJ][2], cdot[NJ][2];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) css[j][0] = css[j][1] = cdot[j][0] = cdot[j][1] = 0.0;
-    double cacc[4][2][2];
-    acc_zero(cacc);
     const int nb = a.nbuf;
-    const int ntile = NT * (NT + 1) / 2;       // tiles are consumed in workspace order: (0,0) (1,0) (1,1) (2,0) ...
-    int tcount = 0;
-    if (tid == 0) bulk_g2s(Wbuf, Lw, TILE_BYTES, &bar[0]);
-    for (int I = 0; I < NT; ++I) {
-        double acc[MI][NJ][2];
-        acc_zero(acc);
-        for (int J = 0; J <= I; ++J, ++tcount) {
-            const int cur = (nb == 2) ? (tcount & 1) : 0;
-            if (nb == 2 && tid == 0 && tcount + 1 < ntile)     // the other buffer was released by the barrier below
-                bulk_g2s(Wbuf + (size_t)(cur ^ 1) * TILE_ELEMS, Lw + (size_t)(tcount + 1) * TILE_ELEMS, TILE_BYTES, &bar[cur ^ 1]);
-            mbar_wait(&bar[cur], (nb == 2) ? ((tcount >> 1) & 1u) : (tcount & 1u));
-            // W_II is lower triangular: columns k > m contribute nothing
-            tile_mma<false, false, false, MI, NJ, TS, CB>(acc, Wbuf + (size_t)cur * TILE_ELEMS, Ks + (size_t)J * TS * CB, wt, 0,
-                                                          (J == I) ? wt.m0 + 8 * MI : TS);
-            __syncthreads();               // everyone done with this buffer before the next bulk copy lands in it
-            if (nb == 1 && tid == 0 && tcount + 1 < ntile)
-                bulk_g2s(Wbuf, Lw + (size_t)(tcount + 1) * TILE_ELEMS, TILE_BYTES, &bar[0]);
+    const long long nblk = (a.M + CB - 1) / CB;
+    const long long ncta = (long long)gridDim.x * gridDim.y, cta = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    double* vpart = a.vpart ? a.vpart + (size_t)cta * NT * NACC * NTHREADS : nullptr;
+
+    for (long long item = cta; item < nblk * a.B; item += ncta) {
+        const int b = (int)(item / nblk), blk = (int)(item - (long long)b * nblk);
+        const Hyper h = decode_hyper(gd, a.theta + (size_t)b * gd.Pk, a.yerr2[b]);
+        const double* Lw = a.wk.Lw + (size_t)b * (NT * (NT + 1) / 2) * TILE_ELEMS;
+        const int c_base = blk * CB;
+        __syncthreads();                   // the previous item is done with tz / tu / part (and the barriers are set up)
+        for (int e = tid; e < CB * D; e += NTHREADS) {
+            const int c = e / D, k = e - c * D;
+            const int gc = c_base + c;
+            const double x = (gc < a.M) ? __ldg(&a.T[(size_t)b * a.T_bstride + (size_t)gc * D + k]) : 0.0;
+            if (k < d) tz[k * CB + c] = x * h.scale[k];
+            if (k == d) tu[c] = x;
         }
+        if (gd.family != 1) for (int c = tid; c < CB; c += NTHREADS) tu[c] = 0.0;
+
+        double pmu[CB / 32];
 #pragma unroll
-        for (int i = 0; i < MI; ++i) {
-            const double dvr = a.dotvec ? __ldg(&a.dotvec[(size_t)b * Np + TS * I + wt.m0 + 8 * i + g]) : 0.0;
+        for (int q = 0; q < CB / 32; ++q) pmu[q] = 0.0;
+        double css[NJ][2], cdot[NJ][2];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j)
+        for (int j = 0; j < NJ; ++j) css[j][0] = css[j][1] = cdot[j][0] = cdot[j][1] = 0.0;
+        double cacc[4][2][2];
+        acc_zero(cacc);
+
+        for (int c0 = 0; c0 < NT; c0 += JC) {
+            const int c1 = (c0 + JC < NT) ? c0 + JC : NT;
+            // ---- observations of the tile rows [c0, c1): scaled coordinates, basis column, alpha ----
+            __syncthreads();               // the W tile buffers of the previous chunk are no longer read
+            const int r0 = TS * c0, nrow = TS * (c1 - c0);
+            for (int e = tid; e < nrow * D; e += NTHREADS) {
+                const int li = e / D, k = e - li * D;
+                const int gi = r0 + li;
+                const double x = (gi < N) ? __ldg(&gd.X[(size_t)gi * D + k]) : 0.0;
+                if (k < d) zs[k * rows_c + li] = x * h.scale[k];
+                if (gd.family == 1 && k == d) us[li] = x;
+            }
+            for (int li = tid; li < nrow; li += NTHREADS) {
+                if (gd.family != 1) us[li] = 0.0;
+                al[li] = a.wk.alpha[(size_t)b * Np + r0 + li];
+            }
+            __syncthreads();
+
+            // ---- cross-covariance panel rows K*^T (obs x cand) + mean partials ----
+#define FAB_PANEL_CASE(DD) case DD: predict_panel<DD, CB>(Ks, zs, us, al, tz, tu, h, gd.family, N, rows_c, c1 - c0, r0, a.M - c_base, etab, pmu); break;
+            switch (d) {
+                FAB_PANEL_CASE(1) FAB_PANEL_CASE(2) FAB_PANEL_CASE(3) FAB_PANEL_CASE(4)
+                FAB_PANEL_CASE(5) FAB_PANEL_CASE(6) FAB_PANEL_CASE(7) FAB_PANEL_CASE(8)
+            }
+#undef FAB_PANEL_CASE
+            fence_proxy_async();           // the coordinate region is about to be overwritten by bulk copies
+            __syncthreads();
+
+            // ---- V_I (+)= sum_{J in chunk, J <= I} W_IJ K*_J, reduced as soon as a row block is complete; W tiles
+            // stream through `nbuf` buffers in the order (I, J) = (c0, c0) (c0+1, c0) (c0+1, c0+1) ... ----
+            int tcount = 0;
+            if (tid == 0) bulk_g2s(Wbuf, Lw + (size_t)tri_index(c0, c0) * TILE_ELEMS, TILE_BYTES, &bar[0]);
+            for (int I = c0; I < NT; ++I) {
+                double acc[MI][NJ][2];
+                if (c0 > 0) {              // rows of V started by the earlier chunks
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    css[j][e] = fma(acc[i][j][e], acc[i][j][e], css[j][e]);
-                    cdot[j][e] = fma(acc[i][j][e], dvr, cdot[j][e]);
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                acc[i][j][e] = vpart[((size_t)I * NACC + (i * NJ + j) * 2 + e) * NTHREADS + tid];
+                } else {
+                    acc_zero(acc);
                 }
-        }
-        if (a.vcol && blk == 0) {
+                const int jhi = (I < c1 - 1) ? I : c1 - 1;
+                for (int J = c0; J <= jhi; ++J, ++tcount) {
+                    const int cur = (nb == 2) ? (tcount & 1) : 0;
+                    // the tile after (I, J) in this chunk's order
+                    int In = I, Jn = J + 1;
+                    if (Jn > jhi) { In = I + 1; Jn = c0; }
+                    const bool more = In < NT;
+                    if (nb == 2 && tid == 0 && more)       // the other buffer was released by the barrier below
+                        bulk_g2s(Wbuf + (size_t)(cur ^ 1) * TILE_ELEMS, Lw + (size_t)tri_index(In, Jn) * TILE_ELEMS, TILE_BYTES,
+                                 &bar[cur ^ 1]);
+                    mbar_wait(&bar[cur], waits[cur] & 1u);
+                    ++waits[cur];
+                    // W_II is lower triangular: columns k > m contribute nothing
+                    tile_mma<false, false, false, MI, NJ, TS, CB>(acc, Wbuf + (size_t)cur * TILE_ELEMS, Ks + (size_t)(J - c0) * TS * CB,
+                                                                  wt, 0, (J == I) ? wt.m0 + 8 * MI : TS);
+                    __syncthreads();       // everyone done with this buffer before the next bulk copy lands in it
+                    if (nb == 1 && tid == 0 && more)
+                        bulk_g2s(Wbuf, Lw + (size_t)tri_index(In, Jn) * TILE_ELEMS, TILE_BYTES, &bar[0]);
+                }
+                if (I >= c1) {             // the later chunks continue this row block
 #pragma unroll
-            for (int i = 0; i < MI; ++i)
+                    for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < NJ; ++j)
+                        for (int j = 0; j < NJ; ++j)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        if (wt.n0 + 8 * j + 2 * t + e == a.vcol_index)
-                            a.vcol[(size_t)b * Np + TS * I + wt.m0 + 8 * i + g] = acc[i][j][e];
-        }
-        if (CB == 64 && want_cov) {
-            acc_store<MI, NJ, CB>(acc, Vscr, wt);
-            __syncthreads();
-            tile_mma<true, false, false, 4, 2, CB, CB>(cacc, Vscr, Vscr, warp_tile(), 0, TS);
-            __syncthreads();
-        }
-    }
-    // reduce the per-thread column partials over the 8 row lanes (g) of the warp
+                            for (int e = 0; e < 2; ++e)
+                                vpart[((size_t)I * NACC + (i * NJ + j) * 2 + e) * NTHREADS + tid] = acc[i][j][e];
+                    continue;
+                }
 #pragma unroll
-    for (int j = 0; j < NJ; ++j)
+                for (int i = 0; i < MI; ++i) {
+                    const double dvr = a.dotvec ? __ldg(&a.dotvec[(size_t)b * Np + TS * I + wt.m0 + 8 * i + g]) : 0.0;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+                    for (int j = 0; j < NJ; ++j)
 #pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                css[j][e] += __shfl_xor_sync(0xffffffffu, css[j][e], o);
-                cdot[j][e] += __shfl_xor_sync(0xffffffffu, cdot[j][e], o);
+                        for (int e = 0; e < 2; ++e) {
+                            css[j][e] = fma(acc[i][j][e], acc[i][j][e], css[j][e]);
+                            cdot[j][e] = fma(acc[i][j][e], dvr, cdot[j][e]);
+                        }
+                }
+                if (a.vcol && blk == 0) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                if (wt.n0 + 8 * j + 2 * t + e == a.vcol_index)
+                                    a.vcol[(size_t)b * Np + TS * I + wt.m0 + 8 * i + g] = acc[i][j][e];
+                }
+                if (CB == 64 && want_cov) {
+                    acc_store<MI, NJ, CB>(acc, Vscr, wt);
+                    __syncthreads();
+                    tile_mma<true, false, false, 4, 2, CB, CB>(cacc, Vscr, Vscr, warp_tile(), 0, TS);
+                    __syncthreads();
+                }
             }
         }
-    const int rg = (CB == 64) ? (w >> 2) : (w >> 1);
-    if (g == 0) {
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) part[w * CB + lane + 32 * q] = pmu[q];
+        // reduce the per-thread column partials over the 8 row lanes (g) of the warp
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = wt.n0 + 8 * j + 2 * t + e;
-                part[(8 + rg) * CB + c] = css[j][e];
-                part[(16 + rg) * CB + c] = cdot[j][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    css[j][e] += __shfl_xor_sync(0xffffffffu, css[j][e], o);
+                    cdot[j][e] += __shfl_xor_sync(0xffffffffu, cdot[j][e], o);
+                }
             }
-    }
-    __syncthreads();
-    if (tid < CB && c_base + tid < a.M) {
-        const int c = tid;
-        double m = 0.0, ss = 0.0, dd = 0.0;
+        const int rg = (CB == 64) ? (w >> 2) : (w >> 1);
+        if (g == 0) {
 #pragma unroll
-        for (int q = 0; q < NWARPS; ++q) m += part[q * CB + c];
-#pragma unroll
-        for (int q = 0; q < NRG; ++q) { ss += part[(8 + q) * CB + c]; dd += part[(16 + q) * CB + c]; }
-        const size_t o = (size_t)b * a.M + c_base + c;
-        if (a.mu) a.mu[o] = m + gd.mean;
-        if (a.var) {
-            const double kss = h.amp * ((gd.family == 1) ? fma(tu[c] * tu[c], h.inv_g2, h.cb) : 1.0);
-            a.var[o] = kss - ss;
-        }
-        if (a.dot) a.dot[o] = dd;
-    }
-    if (CB == 64 && want_cov) {
-        const WarpTile wc = warp_tile();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int c1 = wc.m0 + 8 * i + g, c2 = wc.n0 + 8 * j + 2 * t + e;
-                    if (c1 < a.M && c2 < a.M) {
-                        double r2 = 0.0;
-                        for (int k = 0; k < d; ++k) {
-                            const double dz = tz[k * CB + c1] - tz[k * CB + c2];
-                            r2 = fma(dz, dz, r2);
-                        }
-                        double m, gf;
-                        matern52(r2, m, gf);
-                        double v = h.amp * m;
-                        if (gd.family == 1) v *= fma(tu[c1] * tu[c2], h.inv_g2, h.cb);
-                        a.cov[((size_t)b * a.M + c1) * a.M + c2] = v - cacc[i][j][e];
-                    }
+                    const int c = wt.n0 + 8 * j + 2 * t + e;
+                    part[(8 + rg) * CB + c] = css[j][e];
+                    part[(16 + rg) * CB + c] = cdot[j][e];
                 }
+        }
+        __syncthreads();
+        if (tid < CB && c_base + tid < a.M) {
+            const int c = tid;
+            double m = 0.0, ss = 0.0, dd = 0.0;
+#pragma unroll
+            for (int q = 0; q < NWARPS; ++q) m += part[q * CB + c];
+#pragma unroll
+            for (int q = 0; q < NRG; ++q) { ss += part[(8 + q) * CB + c]; dd += part[(16 + q) * CB + c]; }
+            const size_t o = (size_t)b * a.M + c_base + c;
+            if (a.mu) a.mu[o] = m + gd.mean;
+            if (a.var) {
+                const double kss = h.amp * ((gd.family == 1) ? fma(tu[c] * tu[c], h.inv_g2, h.cb) : 1.0);
+                a.var[o] = kss - ss;
+            }
+            if (a.dot) a.dot[o] = dd;
+        }
+        if (CB == 64 && want_cov) {
+            const WarpTile wc = warp_tile();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c1 = wc.m0 + 8 * i + g, c2 = wc.n0 + 8 * j + 2 * t + e;
+                        if (c1 < a.M && c2 < a.M) {
+                            double r2 = 0.0;
+                            for (int k = 0; k < d; ++k) {
+                                const double dz = tz[k * CB + c1] - tz[k * CB + c2];
+                                r2 = fma(dz, dz, r2);
+                            }
+                            double m, gf;
+                            matern52(r2, m, gf);
+                            double v = h.amp * m;
+                            if (gd.family == 1) v *= fma(tu[c1] * tu[c2], h.inv_g2, h.cb);
+                            a.cov[((size_t)b * a.M + c1) * a.M + c2] = v - cacc[i][j][e];
+                        }
+                    }
+        }
     }
 }
 

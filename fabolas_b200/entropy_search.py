@@ -13,7 +13,7 @@ from ._capi import FAB_FAMILY_M52, FAB_PRIOR_ES
 from .fabolas import lognorm_logpdf
 from .horseshoe import Horseshoe
 from .models import ModelBatch
-from .sampler import DeviceEnsembleSampler, EnsembleSampler
+from .sampler import EnsembleSampler
 
 
 def log_prob_batch(theta, engine):
@@ -37,16 +37,14 @@ def log_prob_batch(theta, engine):
 
 def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None, on_device=True):
     """entropy_search.py:20-85.  on_device (default): the whole chain is one persistent kernel."""
+    engine = engine or runtime.new_engine()
+    if on_device:
+        from .fabolas import _collect_chain, _enqueue_chain
+        return _collect_chain(*_enqueue_chain(engine, X, y, K, burn_in + iterations, FAB_FAMILY_M52, FAB_PRIOR_ES))
     X = np.asarray(X, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
-    engine = engine or runtime.new_engine()
     engine.set_data(FAB_FAMILY_M52, X, y, float(np.mean(y)), float(X.shape[1]))
     ndim = X.shape[1] + 2
-    if on_device:
-        sampler = DeviceEnsembleSampler(K, ndim, engine, FAB_PRIOR_ES)
-        state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, store=False)
-        sampler.reset()
-        return sampler.run_mcmc(state, iterations, store=False).coords
     sampler = EnsembleSampler(K, ndim, log_prob_batch, args=[engine], vectorize=True)
     state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, rstate0=np.random.get_state())
     sampler.reset()

@@ -14,7 +14,7 @@ from ._capi import FAB_FAMILY_M52_BASIS, FAB_PRIOR_FABOLAS
 from .george import GP, ConstantKernel, LinearKernel, Matern52Kernel
 from .horseshoe import Horseshoe
 from .models import ModelBatch
-from .sampler import DeviceEnsembleSampler, EnsembleSampler
+from .sampler import EnsembleSampler
 
 
 def lognorm_logpdf(x, s=1.0):
@@ -62,27 +62,66 @@ def log_likelihood_batch(params, engine):
     return out
 
 
-def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None, on_device=True):
-    """fabolas.py:69-117: K walkers, 100 burn-in + 500 steps, last positions (K, P).  on_device (default): the
-    whole chain is one persistent kernel (DeviceEnsembleSampler); otherwise the emcee-shaped host loop calls the
-    batched GPU likelihood once per half-step."""
+def _enqueue_chain(engine, X, y, K, nsteps, family, prior):
+    """Enqueue the whole stretch-move chain of one model (burn-in and main run are ONE launch: emcee's reset() between
+    them only forgets the stored samples, fabolas.py:106-116) on the engine's stream; nothing is awaited.  numpy's
+    global state picks the seed and the initial positions, in the order DeviceEnsembleSampler consumes it."""
     X = np.asarray(X, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
+    # kernel = 1 * Matern52(axes 0..d-1) [* (Linear(axis d) + Constant(axis d))]; the scalar becomes a ConstantKernel
+    # over all ndim axes, hence amp_mult = ndim
+    engine.set_data(family, X, y, float(np.mean(y)), float(X.shape[1]))
+    ndim = engine.Pk + 1                       # len(kernel) + 1 (the noise)
+    seed = int(np.random.randint(0, 2 ** 31 - 1))
+    p0 = np.random.rand(K, ndim)
+    coords, lp, _, _, _ = engine.mcmc_run(prior, p0, nsteps, seed=seed, store_chain=False)
+    return coords, lp
+
+
+def _collect_chain(coords, lp):
+    lp = lp.cpu().numpy()                      # synchronises the engine's stream
+    if np.any(np.isnan(lp)):
+        raise ValueError("Probability function returned NaN")
+    return coords.cpu().numpy()
+
+
+def sample_hypers(X, y, K=20, burn_in=100, iterations=500, engine=None, on_device=True):
+    """fabolas.py:69-117: K walkers, 100 burn-in + 500 steps, last positions (K, P).  on_device (default): the
+    whole chain is one persistent kernel; otherwise the emcee-shaped host loop calls the batched GPU likelihood
+    once per half-step."""
     engine = engine or runtime.new_engine()
-    # kernel = 1 * Matern52(axes 0..d-1) * (Linear(axis d) + Constant(axis d)); the scalar becomes a
-    # ConstantKernel over all ndim axes, hence amp_mult = ndim
+    if on_device:
+        return _collect_chain(*_enqueue_chain(engine, X, y, K, burn_in + iterations, FAB_FAMILY_M52_BASIS, FAB_PRIOR_FABOLAS))
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
     engine.set_data(FAB_FAMILY_M52_BASIS, X, y, float(np.mean(y)), float(X.shape[1]))
     ndim = X.shape[1] + 3                      # len(kernel) + 1
-    if on_device:
-        sampler = DeviceEnsembleSampler(K, ndim, engine, FAB_PRIOR_FABOLAS)
-        state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, store=False)
-        sampler.reset()
-        return sampler.run_mcmc(state, iterations, store=False).coords
     sampler = EnsembleSampler(K, ndim, log_likelihood_batch, args=[engine], vectorize=True)
     state = sampler.run_mcmc(np.random.rand(K, ndim), burn_in, rstate0=np.random.get_state())
     sampler.reset()
     sampler.run_mcmc(state, iterations)
     return sampler.chain[:, -1]
+
+
+def sample_hypers_pair(Xf, y, X, c, K=20, burn_in=100, iterations=500):
+    """The function-model and the cost-model chains of get_candidate (fabolas.py:131 and :138) are independent: both
+    persistent sampler kernels are enqueued on their own CUDA streams before either is awaited, so that a K = 20
+    ensemble (10 proposals = 10 busy SMs per half-step) shares the GPU with the other instead of running after it."""
+    if not torch.cuda.is_available():          # kernel emulator (tests): one after the other
+        return (sample_hypers(Xf, y, K, burn_in, iterations), sample_hypers(X, c, K, burn_in, iterations))
+    pending = []
+    for XX, yy in ((Xf, y), (X, c)):
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            eng = runtime.new_engine()         # binds the engine to `stream`
+            pending.append((eng, stream, _enqueue_chain(eng, XX, yy, K, burn_in + iterations, FAB_FAMILY_M52_BASIS,
+                                                        FAB_PRIOR_FABOLAS)))
+    out = []
+    for eng, stream, (coords, lp) in pending:
+        with torch.cuda.stream(stream):
+            out.append(_collect_chain(coords, lp))
+        eng.close()
+    return tuple(out)
 
 
 def _model_theta(hypers, ndim):
@@ -103,10 +142,9 @@ def prepare_candidate_search(dataset, bounds, n_hyper_samples=20, n_gen_samples=
     Xf = np.concatenate((X[:, :-1], ((1 - X[:, -1]) ** 2).reshape(-1, 1)), axis=1)    # Q4
     D = X.shape[1]
 
-    logging.info("Sampling hyperparameters for function models...")
-    hypers = sample_hypers(Xf, dataset["y"], K=n_hyper_samples, burn_in=burn_in, iterations=iterations)
-    logging.info("Sampling hyperparameters for cost models...")
-    cost_hypers = sample_hypers(X, dataset["c"], K=n_hyper_samples, burn_in=burn_in, iterations=iterations)
+    logging.info("Sampling hyperparameters for function and cost models...")
+    hypers, cost_hypers = sample_hypers_pair(Xf, dataset["y"], X, dataset["c"], K=n_hyper_samples, burn_in=burn_in,
+                                             iterations=iterations)
 
     theta, noise = _model_theta(hypers, D)
     models = ModelBatch(FAB_FAMILY_M52_BASIS, Xf, dataset["y"], theta, noise, amp_mult=D)   # yerr = sqrt(noise)

@@ -87,7 +87,9 @@ int fab_gp_fit_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int
  * 103,109): T is M x D row-major, shared by all models (per_model = 0) or B x M x D with each model
  * predicting at its own points (per_model = 1: the per-hyper-sample representer points of
  * fabolas.py:180-188).  mu, var: B x M (latent mean / variance, no noise term) or NULL;
- * cov: B x M x M or NULL (full predictive covariance, M <= 64: the reference uses M in {1,50,51}). */
+ * cov: B x M x M or NULL (full predictive covariance, M <= 64: the reference uses M in {1,50,51}).
+ * Any N: up to N = 512 the cross-covariance panel of a candidate block lives in shared memory whole; beyond, it is
+ * generated a few tile rows at a time (acquisitions.py:31 predicts at whatever size the history has grown to). */
 int fab_gp_predict_batch(fab_ctx* ctx, const double* T, int per_model, int M, double* mu, double* var,
                          double* cov);
 
@@ -217,6 +219,9 @@ int fab_ctx_debug_set_mcmc_ctas(fab_ctx* ctx, int n);
 /* Debug / test knob: cap the number of shared-memory tile slots (4..6) so that small problems
  * exercise the L2/HBM tile-streaming path of the fused GP kernel.                                  */
 int fab_ctx_debug_set_max_slots(fab_ctx* ctx, int n);
+/* Debug / test knob: cap the tile rows of the cross-covariance panel the prediction kernel keeps in shared memory
+ * (0 = whatever fits), so that small problems exercise the chunked-panel path of N > 512.              */
+int fab_ctx_debug_set_predict_chunk(fab_ctx* ctx, int jc);
 /* Debug / test knob: make the fused GP kernel stage 64-row coordinate slices per tile (its large-N
  * mode) even when all coordinates would fit in shared memory.                                      */
 int fab_ctx_debug_force_slices(fab_ctx* ctx, int on);

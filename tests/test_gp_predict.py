@@ -98,7 +98,31 @@ def test_predict_requires_fit_emulated(sim_engine):
         sim_engine.predict(np.zeros((2, 1)))
 
 
+@pytest.mark.parametrize("N,D,family,B,M,cov,jc", [(130, 4, 1, 2, 70, False, 1), (200, 3, 0, 1, 40, True, 2), (260, 3, 1, 1, 33, False, 3)])
+def test_predict_chunked_panel_emulated(sim_engine, N, D, family, B, M, cov, jc):
+    """The N > 512 path of the prediction kernel (cross-covariance panel generated `jc` tile rows at a time, partial
+    rows of V parked in the per-CTA scratch, persistent grid) forced at small N."""
+    try:
+        sim_engine.debug_set_predict_chunk(jc)
+        _check_predict(sim_engine, N, D, family, B, M, seed=N, cov=cov)
+    finally:
+        sim_engine.debug_set_predict_chunk(0)
+
+
 # ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,M,cov,jc", [(600, 100, False, 0), (1000, 50, True, 0), (1000, 300, False, 0), (2048, 70, False, 0),
+                                        (512, 257, False, 3), (300, 64, True, 2)])
+def test_predict_large_history_gpu(gpu_engine, N, M, cov, jc):
+    """Prediction beyond N = 512 (the history of a BO run grows every iteration; acquisitions.py:31 predicts at
+    whatever size it has): chunked cross-covariance panel, against the oracle; jc > 0 forces the path at smaller N."""
+    try:
+        gpu_engine.debug_set_predict_chunk(jc)
+        _check_predict(gpu_engine, N, 6, 1, 2, M, seed=N + M, cov=cov)
+    finally:
+        gpu_engine.debug_set_predict_chunk(0)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,D,family,B,M,cov", [(1, 1, 0, 1, 3, True), (20, 2, 0, 3, 1, True), (100, 3, 1, 4, 50, True),
                                                 (100, 3, 1, 4, 51, True), (256, 6, 1, 4, 64, True),

@@ -39,6 +39,15 @@ for name, fn in (("sample_hypers_device_s", lambda: ff.sample_hypers(Xf, d["y"],
                  ("sample_hypers_host_loop_s", lambda: ff.sample_hypers(Xf, d["y"], K=20, on_device=False))):
     fn(); torch.cuda.synchronize(); t0 = time.perf_counter(); h = fn(); torch.cuda.synchronize()
     out[name] = time.perf_counter() - t0
+# both chains of get_candidate (function model + cost model): one after the other vs enqueued on two streams
+def _two_sequential():
+    ff.sample_hypers(Xf, d["y"], K=20); ff.sample_hypers(Xs, d["c"], K=20)
+for name, fn in (("both_chains_sequential_s", _two_sequential),
+                 ("both_chains_concurrent_streams_s", lambda: ff.sample_hypers_pair(Xf, d["y"], Xs, d["c"], K=20))):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+    out[name] = time.perf_counter() - t0
+t0 = time.perf_counter(); prep = ff.prepare_candidate_search(ds(), bounds); torch.cuda.synchronize()
+out["prepare_candidate_search_s (both chains, fit, representers, prior draw, EI, EPMGP, es_setup, cost fit)"] = time.perf_counter() - t0
 # CPU oracle: one information_gain_cost evaluation with the reference's algorithm (K = 20 models, Z = 50, I = 20)
 rng = np.random.default_rng(0)
 K, Z, I = 20, 50, 20
