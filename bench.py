@@ -660,6 +660,17 @@ def leg_configs(cx, args, peak_dmma):
     if exchange == "peer":
         c4["peer_error"] = bool(eng.peer_error())
         eng.peer_free()
+    # prediction at the same history size (the acquisition of a run whose history has grown to N = 2048): 8 resident
+    # models x 4096 candidates per GPU, cross-covariance panel in chunks (gp_predict.cuh)
+    nb_, M_ = 8, 4096
+    eng.fit(th[:nb_], ye[:nb_])
+    Tp = eng.tensor(np.random.default_rng(9 + rank).uniform(w["X"].min(0), w["X"].max(0), (M_, w["D"])))
+    ms = cx.median_ms(lambda: eng.predict(Tp, want_var=True), 1, 3)
+    Fp = N * N + N * (3 * d + 38)
+    tf = Fp * M_ * nb_ * world / (ms * 1e-3) / 1e12
+    c4["predict mean+var"] = {"models_per_gpu": nb_, "candidates_per_gpu": M_, "ms_per_sweep": ms,
+                              "candidate_model_pairs_per_s": M_ * nb_ * world / (ms * 1e-3), "tflops_aggregate": tf,
+                              "frac_fp64_tensor_peak": tf / (peak_dmma * world)}
     out["configs[4] N=2048"] = c4
     eng.close()
 

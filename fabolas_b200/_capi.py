@@ -45,7 +45,7 @@ SIGNATURES = {
     "fab_epmgp_joint_min_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fab_es_setup": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int]),
     "fab_es_information_gain_batch": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
-    "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
+    "fab_kernel_matrix": (_c_int, [_vp, _c_int, _c_int, _c_dbl, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_dbl, _vp, _vp]),
     "fab_gp_prior_draw_batch": (_c_int, [_vp, _vp, _c_int, ctypes.c_ulonglong, _vp, _vp, _vp]),
     "fab_ei_batch": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp]),
     "fab_peer_alloc": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp]),
@@ -335,7 +335,7 @@ class Engine:
         return (ig, flag, mm, mv) if return_mixture else (ig, flag)
 
     def kernel_matrix(self, family: int, theta, Xa, Xb=None, amp_mult: Optional[float] = None, nu_code: int = 0,
-                      grad: bool = False):
+                      grad: bool = False, nu: float = 0.0):
         """K (B, Na, Nb) [, dK (B, Na, Nb, Pk)] of k(Xa, Xb) for every row of theta."""
         Xa = self.tensor(Xa)
         Xb = Xa if Xb is None else self.tensor(Xb)
@@ -348,7 +348,7 @@ class Engine:
         amp_mult = float(D if amp_mult is None else amp_mult)
         K = self.empty(B, Na, Nb)
         dK = self.empty(B, Na, Nb, Pk) if grad else None
-        self._check(self.lib.fab_kernel_matrix(self._ctx, family, nu_code, _ptr(theta), B, _ptr(Xa), Na, _ptr(Xb), Nb, D,
+        self._check(self.lib.fab_kernel_matrix(self._ctx, family, nu_code, float(nu), _ptr(theta), B, _ptr(Xa), Na, _ptr(Xb), Nb, D,
                                                amp_mult, _ptr(K), _ptr(dK)), "fab_kernel_matrix")
         return (K, dK) if grad else K
 

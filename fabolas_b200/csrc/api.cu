@@ -575,17 +575,18 @@ int fab_es_information_gain_batch(fab_ctx* c, const double* Xc, int M, double* i
     return FAB_OK;
 }
 
-int fab_kernel_matrix(fab_ctx* c, int family, int nu_code, const double* theta, int B, const double* Xa, int Na,
+int fab_kernel_matrix(fab_ctx* c, int family, int nu_code, double nu, const double* theta, int B, const double* Xa, int Na,
                       const double* Xb, int Nb, int D, double amp_mult, double* K, double* dK) {
     if (!c) return FAB_EINVAL;
     if (!theta || !Xa || !Xb || !K || B < 1 || Na < 1 || Nb < 1) return fail(c, FAB_EINVAL, "bad argument");
     if (family != FAB_FAMILY_M52 && family != FAB_FAMILY_M52_BASIS) return fail(c, FAB_EINVAL, "unknown family");
-    if (nu_code < 0 || nu_code > 3) return fail(c, FAB_EINVAL, "nu_code must be 0..3");
+    if (nu_code < 0 || nu_code > 4) return fail(c, FAB_EINVAL, "nu_code must be 0..4");
+    if (nu_code == 4 && (!(nu > 0.0) || dK)) return fail(c, FAB_EINVAL, "general nu: nu > 0 and no analytic gradient");
     const int d = family == FAB_FAMILY_M52_BASIS ? D - 1 : D;
     if (d < 1 || d > MAX_D) return fail(c, FAB_EINVAL, "need 1 <= d <= 8 Matern axes");
     FAB_CUDA(c, cudaSetDevice(c->device));
     KmatArgs a;
-    a.family = family; a.D = D; a.d = d; a.Pk = family == FAB_FAMILY_M52_BASIS ? d + 3 : d + 1; a.nu_code = nu_code;
+    a.family = family; a.D = D; a.d = d; a.Pk = family == FAB_FAMILY_M52_BASIS ? d + 3 : d + 1; a.nu_code = nu_code; a.nu = nu;
     a.amp_mult = amp_mult; a.theta = theta; a.Xa = Xa; a.Na = Na; a.Xb = Xb; a.Nb = Nb; a.K = K; a.dK = dK;
     const long long n = (long long)Na * Nb;
     FAB_LAUNCH(kmat_kernel, dim3((unsigned)((n + 255) / 256), B), 256, 0, c->stream, a);

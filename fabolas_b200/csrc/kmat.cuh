@@ -13,6 +13,7 @@ namespace fab {
 
 struct KmatArgs {
     int family, D, d, Pk, nu_code;
+    double nu;             // nu_code 4: the smoothness of the general Matern kernel
     double amp_mult;
     const double* theta;   // B x Pk
     const double* Xa; int Na;
@@ -21,9 +22,33 @@ struct KmatArgs {
     double* dK;            // B x Na x Nb x Pk or null
 };
 
-__device__ __forceinline__ void radial(int nu_code, double r2, double& m, double& gfac) {
+// Modified Bessel function of the second kind K_nu(x), x > 0, any real nu >= 0 (the reference's general-nu branch
+// calls scipy.special.kv, ard.py:129-135): K_nu(x) = int_0^inf exp(-x cosh t) cosh(nu t) dt by the trapezoid rule, which
+// converges geometrically for this entire integrand: step min(0.2, 0.7 / sqrt(x)) (error ~ exp(-2 pi^2 / (x h^2)) resp.
+// exp(-pi^2 / h)), summed until the terms have dropped 1e-18 below the sum past the peak of the integrand.
+__device__ inline double bessel_k(double nu, double x) {
+    const double h = fmin(0.2, 0.7 / sqrt(x));
+    const double t_peak = asinh(nu / x);                       // maximum of nu t - x cosh t
+    double sum = 0.5 * exp(-x);                                 // t = 0 with the trapezoid weight 1/2
+    for (int i = 1; i < 200000; ++i) {
+        const double t = i * h, c = x * cosh(t);
+        const double term = 0.5 * (exp(nu * t - c) + exp(-nu * t - c));
+        sum += term;
+        if (t > t_peak && term < 1e-18 * sum) break;
+    }
+    return h * sum;
+}
+
+__device__ __forceinline__ void radial(int nu_code, double r2, double& m, double& gfac, double nu = 0.0) {
     // m = k(r2), gfac = -dk/dr2
-    if (nu_code == 0) {
+    if (nu_code == 4) {
+        // ard.py:129-135: strict zeros get eps, tmp = sqrt(2 nu) dist, K = 2^(1-nu) / Gamma(nu) * tmp^nu * K_nu(tmp)
+        double dist = sqrt(r2);
+        if (dist == 0.0) dist += 2.220446049250313e-16;
+        const double tmp = sqrt(2.0 * nu) * dist;
+        m = (exp2(1.0 - nu) / tgamma(nu)) * pow(tmp, nu) * bessel_k(nu, tmp);
+        gfac = 0.0;            // (the reference differentiates this branch numerically, ard.py:168-173)
+    } else if (nu_code == 0) {
         matern52(r2, m, gfac);
     } else if (nu_code == 1) {
         const double r = sqrt(3.0 * r2), e = exp(-r);
@@ -56,7 +81,7 @@ __global__ void __launch_bounds__(256) kmat_kernel(KmatArgs a) {
         }
     }
     double m, gf;
-    radial(a.nu_code, r2, m, gf);
+    radial(a.nu_code, r2, m, gf, a.nu);
     double uu = 0.0, cb = 1.0, beta = 1.0;
     if (a.family == 1) {
         uu = a.Xa[(size_t)i * a.D + a.d] * a.Xb[(size_t)j * a.D + a.d] * exp(-th[1 + a.d]);

@@ -1,7 +1,6 @@
 """Entropy Search candidate search on the CUDA engine (reference: entropy_search.py), Matern-only
 kernel, no dataset-size dimension.  Quirk numbers refer to SURVEY.md section 3.4."""
 import logging
-import time
 
 import numpy as np
 import torch
@@ -75,27 +74,3 @@ def entropy_search(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_inno
     logging.info("Ready to optimize Information Gain")
     return minimize(fun=lambda x: -information_gain(x, models), x0=X[np.argmax(y)], method="L-BFGS-B",
                     bounds=bounds, options={"maxiter": maxiter})
-
-
-def es(obj_function, prior, bounds, iterations=10):
-    """entropy_search.py:172-229 without the hard-coded Colab save path."""
-    wallclock_time = time.time()
-    progress = {"config": np.empty((0, prior["X"].shape[1])), "value": np.empty((0, 1)), "time": np.empty((0, 1))}
-    for i in range(iterations):
-        logging.info(f"---- ES: Iteration #{i+1} ----")
-        result = None
-        while result is None:
-            try:
-                result = entropy_search(prior, bounds)
-            except ArithmeticError:
-                logging.warning("Bad surrogate, trying again..")
-        y = obj_function(result.x)
-        iteration_time = time.time() - wallclock_time
-        prior["X"] = np.vstack([prior["X"], result.x])
-        prior["y"] = np.vstack([np.asarray(prior["y"]).reshape(-1, 1), np.array([[y]])])
-        progress["config"] = np.vstack([progress["config"], result.x])
-        progress["value"] = np.vstack([progress["value"], np.array([[y]])])
-        progress["time"] = np.vstack([progress["time"], np.array([[iteration_time]])])
-    prior["y_best"] = max(prior["y"])
-    prior["X_best"] = prior["X"][np.argmax(prior["y"])]
-    return prior, progress

@@ -49,25 +49,3 @@ def get_candidate(prior, bounds, n_gen_samples=100, engine=None):
     if int(index[0]) < 0:
         raise ArithmeticError("expected improvement has no maximiser over the candidate set")
     return X_samples[int(index[0])]
-
-
-def ei(obj_function, prior, bounds=None, n_iter=10):
-    """expected_improvement.py:13-67 without the hard-coded Colab save path."""
-    import time
-    wallclock_time = time.time()
-    progress = {"config": np.empty((0, prior["X"].shape[1])), "value": np.empty((0, 1)), "time": np.empty((0, 1))}
-    for _ in range(n_iter):
-        X_candidate = get_candidate(prior, bounds)
-        if bounds is not None:
-            for i, b in enumerate(bounds):
-                X_candidate[i] = np.clip(X_candidate[i], b[0], b[1])
-        y_candidate = obj_function(X_candidate)
-        iteration_time = time.time() - wallclock_time
-        prior["X"] = np.vstack([prior["X"], X_candidate])
-        prior["y"] = np.vstack([np.asarray(prior["y"]).reshape(-1, 1), np.array([[y_candidate]])])
-        progress["config"] = np.vstack([progress["config"], X_candidate])
-        progress["value"] = np.vstack([progress["value"], np.array([[y_candidate]])])
-        progress["time"] = np.vstack([progress["time"], np.array([[iteration_time]])])
-    prior["y_best"] = max(prior["y"])
-    prior["X_best"] = prior["X"][np.argmax(prior["y"])]
-    return prior, progress

@@ -2,7 +2,6 @@
 reference's fabolas.py, with the MCMC likelihood, model fitting, EPMGP and information gain
 evaluated in batches on the GPU.  Quirk numbers refer to SURVEY.md section 3.4."""
 import logging
-import time
 
 import numpy as np
 import torch
@@ -195,44 +194,6 @@ def get_candidate(dataset, bounds, n_hyper_samples=20, n_gen_samples=50, n_innov
                         bounds=bounds, options=opts)
     return minimize(fun=lambda x: -information_gain_cost(x, cost_models, models), x0=starting_point,
                     method="L-BFGS-B", bounds=bounds, options=opts)
-
-
-def fabolas(obj_function, prior, bounds, iterations=10, **kwargs):
-    """fabolas.py:267-327 (outer loop; the objective is the expensive black box, not the path)."""
-    prior["min_time"] = 0
-    if min(prior["c"]) < 0:
-        prior["min_time"] = np.array(min(prior["c"]))
-        prior["c"] += -prior["min_time"]
-    wallclock_time = time.time()
-    progress = {"config": np.empty((0, prior["X"].shape[1] + 1)), "value": np.empty((0, 1)),
-                "time": np.empty((0, 1)), "size": np.empty((0, 1))}
-    for i in range(iterations):
-        logging.info(f"---- FABOLAS: Iteration #{i+1} ----")
-        result = None
-        while result is None:
-            try:
-                result = get_candidate(prior, bounds, **kwargs)
-            except ArithmeticError:
-                logging.warning("Bad surrogate, trying again..")
-        logging.info(f"Evaluating function at {result.x}")
-        cost = time.time()
-        y = obj_function(result.x)
-        cost = time.time() - cost
-        iteration_time = time.time() - wallclock_time
-        prior["X"] = np.vstack([prior["X"], result.x[:-1]])
-        prior["y"] = np.append(prior["y"], np.array([y]))
-        prior["size"] = np.append(prior["size"], np.array([result.x[-1]]))
-        prior["c"] = np.append(prior["c"], np.array([np.log10(cost) - prior["min_time"]]))
-        if min(prior["c"]) < 0:
-            prior["c"] += -(np.log10(cost) - prior["min_time"])
-            prior["min_time"] = np.array(np.log10(cost))
-        progress["config"] = np.vstack([progress["config"], result.x])
-        progress["value"] = np.append(progress["value"], np.array([y]))
-        progress["time"] = np.append(progress["time"], np.array([iteration_time]))
-        progress["size"] = np.append(progress["size"], np.array([result.x[-1]]))
-    prior["y_best"] = max(prior["y"])
-    prior["X_best"] = prior["X"][np.argmax(prior["y"])]
-    return prior, progress
 
 
 def make_gp(X, mean):

@@ -138,10 +138,12 @@ int fab_es_information_gain_batch(fab_ctx* ctx, const double* Xc, int M, double*
 
 /* Materialised covariance matrices k(Xa, Xb) for B hyper-parameter rows (and, optionally, their
  * derivatives with respect to every theta_k): the kernel object surface of ard.py
- * (AutomaticRelevanceDetermination.__call__, ard.py:82-180: nu_code 0 = 2.5, 1 = 1.5, 2 = 0.5, 3 = inf
- * on r2 = sum_k (x_k - x'_k)^2 / M_k) and george's kernel.get_value / get_gradient.
+ * (AutomaticRelevanceDetermination.__call__, ard.py:82-180: nu_code 0 = 2.5, 1 = 1.5, 2 = 0.5, 3 = inf, 4 = the
+ * general Matern kernel of smoothness `nu` with the Bessel function K_nu evaluated on the device (ard.py:129-135; no
+ * analytic gradient, as in the reference), on r2 = sum_k (x_k - x'_k)^2 / M_k) and george's kernel.get_value /
+ * get_gradient.
  *   Xa Na x D, Xb Nb x D, theta B x Pk  ->  K B x Na x Nb ; dK B x Na x Nb x Pk or NULL.           */
-int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, const double* theta, int B, const double* Xa,
+int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, double nu, const double* theta, int B, const double* Xa,
                       int Na, const double* Xb, int Nb, int D, double amp_mult, double* K, double* dK);
 
 /* Multi-GPU likelihood step with the exchange fused into the kernel (walkers sharded across

@@ -175,13 +175,20 @@ def ard_cases():
     out = {}
     for n in (2, 4, 6):
         X = rng.standard_normal((n, n)); Y = rng.standard_normal((n, n)); ls = rng.uniform(0.5, 2.0, n)
-        for nu in (0.5, 1.5, 2.5, np.inf):
+        for nu in (0.5, 1.5, 2.5, np.inf, 1.0, 2.0, 3.3):          # the last three: general branch (Bessel K_nu, ard.py:129-135)
             k = ref_ard.AutomaticRelevanceDetermination(length_scale=ls, nu=nu)
             tag = f"n{n}_nu{nu}"
             out[tag + "_Kxy"] = k(X, Y)
-            if nu != 0.5:
-                K, G = k(X, eval_gradient=True)
-                out[tag + "_K"], out[tag + "_G"] = K, G
+            if nu in (1.0, 2.0, 3.3):                              # the reference's gradient of this branch raises NameError
+                out[tag + "_K"] = k(X)                             # (ard.py:173 calls _approx_fprime, never imported)
+                continue
+            K, G = k(X, eval_gradient=True)
+            if nu == 0.5:                                          # ard.py:156-160 leaves the diagonal unset (0/0)
+                G = G.copy(); G[np.arange(n), np.arange(n), :] = 0.0
+            out[tag + "_K"], out[tag + "_G"] = K, G
+        # a pair of coinciding points in k(X, Y): the strict-zero distance of the general branch (ard.py:131)
+        Yd = Y.copy(); Yd[0] = X[0]
+        out[f"n{n}_nu2.0_Kxy_dup"] = ref_ard.AutomaticRelevanceDetermination(length_scale=ls, nu=2.0)(X, Yd)
         out[f"n{n}_X"], out[f"n{n}_Y"], out[f"n{n}_ls"] = X, Y, ls
     np.savez_compressed(os.path.join(HERE, "ard_ref.npz"), **out)
     print("ard_ref.npz")
@@ -213,6 +220,9 @@ def gp_cases():
 
 
 if __name__ == "__main__":
+    if "--ard-only" in sys.argv:
+        ard_cases()
+        sys.exit(0)
     if "--full-only" in sys.argv:          # the ~2 min full-size information-gain case alone
         acquisition_case_full()
         sys.exit(0)

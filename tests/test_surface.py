@@ -190,14 +190,28 @@ def _ard_and_epmgp_and_horseshoe(rt):
     g = golden("ard_ref.npz")
     for n in (2, 4, 6):
         X, Y, ls = g[f"n{n}_X"], g[f"n{n}_Y"], g[f"n{n}_ls"]
-        for nu in (0.5, 1.5, 2.5, np.inf):
+        for nu in (0.5, 1.5, 2.5, np.inf, 1.0, 2.0, 3.3):
             k = AutomaticRelevanceDetermination(length_scale=ls, nu=nu)
             tag = f"n{n}_nu{nu}"
             assert np.allclose(k(X, Y), g[tag + "_Kxy"], rtol=1e-11, atol=1e-14)
-            if nu != 0.5:
+            if nu in (1.0, 2.0, 3.3):
+                # general branch: Bessel K_nu on the device vs the reference's scipy.special.kv (ard.py:129-135); its
+                # gradient raises NameError in the reference (ard.py:173) -- here the forward differences it intended,
+                # checked against central differences of the kernel itself
+                assert np.allclose(k(X), g[tag + "_K"], rtol=1e-11, atol=1e-14)
                 K, G = k(X, eval_gradient=True)
-                assert np.allclose(K, g[tag + "_K"], rtol=1e-11, atol=1e-14)
-                assert np.allclose(G, g[tag + "_G"], rtol=1e-10, atol=1e-13)
+                h = 1e-5
+                for q in range(n):
+                    lp, lm = ls.copy(), ls.copy()
+                    lp[q] *= np.exp(h); lm[q] *= np.exp(-h)
+                    fd = (AutomaticRelevanceDetermination(lp, nu=nu)(X) - AutomaticRelevanceDetermination(lm, nu=nu)(X)) / (2 * h)
+                    assert np.allclose(G[..., q], fd, rtol=1e-3, atol=2e-5)
+                continue
+            K, G = k(X, eval_gradient=True)
+            assert np.allclose(K, g[tag + "_K"], rtol=1e-11, atol=1e-14)
+            assert np.allclose(G, g[tag + "_G"], rtol=1e-10, atol=1e-13)     # nu = 0.5: diagonal 0 (0/0 in the reference)
+        Yd = Y.copy(); Yd[0] = X[0]                              # coinciding points: the strict-zero distance (ard.py:131)
+        assert np.allclose(AutomaticRelevanceDetermination(ls, nu=2.0)(X, Yd), g[f"n{n}_nu2.0_Kxy_dup"], rtol=1e-11, atol=1e-14)
     assert "AutomaticRelevanceDetermination(length_scale=[" in repr(AutomaticRelevanceDetermination([1.0, 2.0], nu=2.5))
     ge = golden("epmgp_ref.npz")
     logP, dMu, dSg, dMM = fep.joint_min(ge["z12_mu"], ge["z12_S"], with_derivatives=True)
