@@ -42,11 +42,14 @@ WALKERS_PER_GPU = 128
 WORKLOAD = ("BASELINE configs[1]: CNN-CIFAR10 space (5 hyper-parameters) + s, N=256, D=6, P=9, 128 walkers per GPU, "
             "Matern52 x (linear+const) basis kernel, FP64")
 # dram__bytes_read.sum + dram__bytes_write.sum of one gp_dag_kernel launch from the committed ncu --set full capture
-TRAFFIC_BYTES_PER_LAUNCH = 186880 + 1583360
-TRAFFIC_SOURCE = ("profiles/r01aj_ncu_full_raw.csv: dram__bytes_read.sum 187 KB + dram__bytes_write.sum 1.58 MB per "
+TRAFFIC_BYTES_PER_LAUNCH = 168960 + 1181952
+TRAFFIC_SOURCE = ("profiles/r02k_ncu_full_raw.csv: dram__bytes_read.sum 169 KB + dram__bytes_write.sum 1.18 MB per "
                   "launch of 128 evals (algorithmic bytes 128 x 14.4 KB = 1.84 MB; tiles stream through L2 only)")
-ES_TRAFFIC_BYTES_PER_LAUNCH = None      # es_entropy_kernel; filled from the committed capture (profiles/)
-ES_TRAFFIC_SOURCE = None
+# es_entropy_kernel: one launch = 2048 candidates x 128 models; reads the per-model coefficients / innovations and
+# the per-(candidate, model) scalars, writes 2 MB of partial sums (absorbed by L2 during the capture)
+ES_TRAFFIC_BYTES_PER_LAUNCH = 3663616 + 0
+ES_TRAFFIC_SOURCE = ("profiles/r02k_es_entropy_ncu_full_raw.csv: dram__bytes_read.sum 3.66 MB + dram__bytes_write.sum 0 per launch "
+                     "(algorithmic bytes: 128 x 11.4 KB of model state + 2 x 2 MB of per-pair scalars in / partials out)")
 # FP64-pipe instructions of es_entropy_kernel per (candidate, model, innovation, column, row) element -- counted in
 # the source and checked against the SASS of the inner loops
 ES_FP64_INSTR_PER_ELEMENT = 11
