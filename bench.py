@@ -586,10 +586,19 @@ def leg_configs(cx, args, peak_dmma):
     N, d, P = w["N"], w["D"] - 1, w["theta"].shape[1] + 1
     c0 = {"N": N, "walkers": 20}
     for grad in (False, True):
-        ms = cx.median_ms(lambda: eng.loglik(th, ye, grad=grad), 5, 30)
+        # the kernel's own duration (CUDA events inside the library); a single launch after a synchronisation also
+        # pays the host's dispatch (~18 us of Python / ctypes), reported next to it
+        ms_call = cx.median_ms(lambda: eng.loglik(th, ye, grad=grad), 5, 30)
+        eng.set_timing(True)
+        kt = []
+        for _ in range(30):
+            eng.loglik(th, ye, grad=grad); kt.append(eng.get_timing()[0])
+        eng.set_timing(False)
+        ms = cx.max_over_ranks(float(np.median(kt)))
         F = flops_llg(N, d, P) if grad else flops_ll(N, d)
         tf = F * 20 / (ms * 1e-3) / 1e12
-        c0["ll+grad" if grad else "ll"] = {"us_per_batch": ms * 1e3, "evals_per_s": 20 / (ms * 1e-3), "tflops": tf,
+        c0["ll+grad" if grad else "ll"] = {"us_per_batch": ms * 1e3, "us_per_call_incl_host_dispatch": ms_call * 1e3,
+                                           "evals_per_s": 20 / (ms * 1e-3), "tflops": tf,
                                            "frac_fp64_tensor_peak": tf / peak_dmma,
                                            "frac_of_the_20_busy_sms": tf / (peak_dmma * 20 / 148)}
     p0 = eng.tensor(np.random.default_rng(5).uniform(0, 1, (20, P)))

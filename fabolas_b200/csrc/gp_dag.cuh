@@ -426,7 +426,11 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         if (wo > 0) {
             // chain op c publishes two events: 2c + 1 (tiles final) and 2c + 2 (vectors); a panel solve that only
             // waits for its own diagonal tile starts on the first and takes z before its epilogue
+#ifdef FAB_TRSM_EARLY
             const int need = (type == DOP_TRSM && wo == J + 1) ? 2 * wo - 1 : 2 * wo;
+#else
+            const int need = 2 * wo;
+#endif
             if (lane == 0) spin_until(&sync[1], need);
             __syncwarp();
         }
