@@ -39,6 +39,33 @@ def _worker(rank, size, port, lib, out):
         ei, bv, bi = eng.expected_improvement(mu[:1], var[:1], np.array([y.max()]))
         assert idx == int(bi[0]) and abs(val - float(bv[0])) < 1e-15
         assert fd.shard_range(5, 0, 2) == (0, 3) and fd.shard_range(5, 1, 2) == (3, 5)
+        # np.argmax semantics across shards: first occurrence of the maximum; the first NaN is the maximum; a rank
+        # without candidates does not take part
+        vals = torch.tensor([0.5, 2.0, 1.0, 2.0, 0.1, 2.0, 0.3])
+        lo, hi = fd.shard_range(7, rank, size)
+        assert fd.sharded_argmax(vals[lo:hi], lo) == (2.0, 1)
+        vals[5] = float("nan")
+        v, i = fd.sharded_argmax(vals[lo:hi], lo)
+        assert np.isnan(v) and i == 5 == int(np.argmax(vals.numpy()))
+        vals[0] = float("nan")
+        v, i = fd.sharded_argmax(vals[lo:hi], lo)
+        assert np.isnan(v) and i == 0
+        one = torch.tensor([3.0])                          # one candidate in all: rank 1 holds nothing
+        lo, hi = fd.shard_range(1, rank, size)
+        assert fd.sharded_argmax(one[lo:hi], lo) == (3.0, 0)
+        ig_ref = None
+        # candidate-sharded information gain needs the Entropy-Search state: small setup, same on both ranks
+        Z, I = 5, 3
+        reps = rng.uniform(0, 1, (2, Z, D)); Omega = rng.standard_normal((2, I, Z))
+        mu_r, _, cov_r = eng.predict(reps, want_var=True, want_cov=True)
+        cov_c = torch.clamp(cov_r, min=2.2e-16)
+        pm = eng.joint_min(mu_r, cov_c)
+        U = torch.full((2, Z), 0.1, dtype=torch.float64)
+        eng.es_setup(reps, cov_r, pm[:4], U, Omega)
+        Xc = rng.uniform(0, 1, (9, D))
+        ig, flag = fd.sharded_information_gain(eng, Xc)
+        ig_ref, flag_ref = eng.information_gain(Xc)
+        assert torch.equal(ig, ig_ref) and torch.equal(flag, flag_ref)
         out[rank] = 1
     finally:
         dist.destroy_process_group()
