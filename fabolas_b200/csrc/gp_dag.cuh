@@ -91,59 +91,62 @@ __device__ __forceinline__ void spin_until(int* p, int target) {
 // Covariance tile (I, J) straight into the DMMA accumulator fragment layout (16 entries per thread).
 // Four passes of four entries (two rows x two adjacent columns) keep the register footprint small enough
 // for the four Matern chains of a pass to overlap; evaluation is branch-free (padding and the strictly-upper
-// blocks of a diagonal tile are selected afterwards: identity resp. zero).
+// blocks of a diagonal tile are selected afterwards: identity resp. zero).  The pass index is a template
+// parameter: with a run-time pass loop the accumulator registers could only be addressed through a switch, and 40 %
+// of the 439 instructions of a pass were register moves and selects (the ops are issue-bound, not FP64-bound).
+template <int DD, int Q>
+__device__ __forceinline__ void build_pass(double (&acc)[4][2][2], const double* zr_s, const double* zc_s,
+                                           const double* ur_s, const double* uc_s, int ldz, const Hyper& h, int N,
+                                           bool basis, double cb, int I, int J, WarpTile wt, const double* __restrict__ etab) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    constexpr int ip = Q >> 1, j = Q & 1;
+    const int lj0 = wt.n0 + 8 * j + 2 * t;
+    const int bcol = (wt.n0 >> 3) + j;
+    // diagonal tile: both 8x8 blocks of this pass lie above the block diagonal -> zero, nothing to evaluate
+    if (I == J && bcol > (wt.m0 >> 3) + 2 * ip + 1) {
+        acc[2 * ip][j][0] = acc[2 * ip][j][1] = acc[2 * ip + 1][j][0] = acc[2 * ip + 1][j][1] = 0.0;
+        return;
+    }
+    double2 zc[DD];
+#pragma unroll
+    for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
+    const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int li = wt.m0 + 8 * (2 * ip + r) + g;
+        const int gi = TS * I + li;
+        const bool upper = I == J && bcol > (li >> 3);
+        double zr[DD];
+#pragma unroll
+        for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
+        const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int gj = TS * J + lj0 + e;
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DD; ++k) {
+                const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                r2 = fma(dz, dz, r2);
+            }
+            double v = h.amp * matern52_fast_value(r2, etab) * fma(ur, e ? uc.y : uc.x, cb);
+            v = (gi == gj) ? v + h.diag_add : v;
+            v = (gi >= N || gj >= N) ? ((gi == gj) ? 1.0 : 0.0) : v;
+            acc[2 * ip + r][j][e] = upper ? 0.0 : v;
+        }
+    }
+}
 template <int DD>
 __device__ __forceinline__ void build_acc(double (&acc)[4][2][2], const double* zr_s, const double* zc_s,
                                           const double* ur_s, const double* uc_s, int ldz, const Hyper& h, int N,
                                           int family, int I, int J, WarpTile wt, const double* __restrict__ etab) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const bool basis = family == 1;
     const double cb = basis ? h.cb : 1.0;
-#pragma unroll 1      // two or four passes in flight measured no faster (259 / 260 us against 256), with spills
-    for (int q = 0; q < 4; ++q) {
-        const int ip = q >> 1, j = q & 1;
-        const int lj0 = wt.n0 + 8 * j + 2 * t;
-        const int bcol = (wt.n0 >> 3) + j;
-        double tmp[2][2];
-        tmp[0][0] = tmp[0][1] = tmp[1][0] = tmp[1][1] = 0.0;
-        // diagonal tile: both 8x8 blocks of this pass lie above the block diagonal -> zero, nothing to evaluate
-        if (!(I == J && bcol > (wt.m0 >> 3) + 2 * ip + 1)) {
-            double2 zc[DD];
-#pragma unroll
-            for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
-            const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int li = wt.m0 + 8 * (2 * ip + r) + g;
-                const int gi = TS * I + li;
-                const bool upper = I == J && bcol > (li >> 3);
-                double zr[DD];
-#pragma unroll
-                for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
-                const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int gj = TS * J + lj0 + e;
-                    double r2 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < DD; ++k) {
-                        const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
-                        r2 = fma(dz, dz, r2);
-                    }
-                    double v = h.amp * matern52_fast_value(r2, etab) * fma(ur, e ? uc.y : uc.x, cb);
-                    v = (gi == gj) ? v + h.diag_add : v;
-                    v = (gi >= N || gj >= N) ? ((gi == gj) ? 1.0 : 0.0) : v;
-                    tmp[r][e] = upper ? 0.0 : v;
-                }
-            }
-        }
-        switch (q) {                        // static accumulator indices
-        case 0: acc[0][0][0] = tmp[0][0]; acc[0][0][1] = tmp[0][1]; acc[1][0][0] = tmp[1][0]; acc[1][0][1] = tmp[1][1]; break;
-        case 1: acc[0][1][0] = tmp[0][0]; acc[0][1][1] = tmp[0][1]; acc[1][1][0] = tmp[1][0]; acc[1][1][1] = tmp[1][1]; break;
-        case 2: acc[2][0][0] = tmp[0][0]; acc[2][0][1] = tmp[0][1]; acc[3][0][0] = tmp[1][0]; acc[3][0][1] = tmp[1][1]; break;
-        default: acc[2][1][0] = tmp[0][0]; acc[2][1][1] = tmp[0][1]; acc[3][1][0] = tmp[1][0]; acc[3][1][1] = tmp[1][1]; break;
-        }
-    }
+    // (the warp barriers keep the compiler from overlapping the passes, which costs registers and gained nothing)
+    build_pass<DD, 0>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab); __syncwarp();
+    build_pass<DD, 1>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab); __syncwarp();
+    build_pass<DD, 2>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab); __syncwarp();
+    build_pass<DD, 3>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab);
 }
 
 // Contract one 64x64 tile of (alpha alpha^T - K^-1), held in this warp's DMMA accumulator fragment, with
@@ -151,79 +154,88 @@ __device__ __forceinline__ void build_acc(double (&acc)[4][2][2], const double* 
 // pass as in build_acc.  Diagonal tiles: weight 2 below the diagonal 8x8 blocks, 1 on them, 0 above.
 // The nine partial sums of the warp go to gsum[warp][.] (fixed order => deterministic):
 //   [0] log_c0, [1..DD] log_M_k, [MAX_D+1] log_gamma2, [MAX_D+2] log_cb, [MAX_PK] yerr2.
+struct ContractSums {            // per-thread partial sums of one contraction
+    double g0, gg2, gcb, gtr;
+};
+template <int DD, int Q>
+__device__ __forceinline__ void contract_pass(const double (&acc)[4][2][2], ContractSums& cs, double (&gm)[DD],
+                                              const double* zr_s, const double* zc_s, const double* ur_s,
+                                              const double* uc_s, const double* al_r, const double* al_c, int ldz,
+                                              const Hyper& h, int N, bool basis, double cb, int I, int J, WarpTile wt,
+                                              const double* __restrict__ etab) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    constexpr int ip = Q >> 1, j = Q & 1;
+    const int lj0 = wt.n0 + 8 * j + 2 * t;
+    const int bcol = (wt.n0 >> 3) + j;
+    if (I == J && bcol > (wt.m0 >> 3) + 2 * ip + 1) return;     // weight 0 on both blocks of this pass
+    double2 zc[DD];
+#pragma unroll
+    for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
+    const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
+    const double2 ac = *reinterpret_cast<const double2*>(&al_c[lj0]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int li = wt.m0 + 8 * (2 * ip + r) + g;
+        const int gi = TS * I + li;
+        const int brow = li >> 3;
+        double zr[DD];
+#pragma unroll
+        for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
+        const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
+        const double ar = al_r[li];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int gj = TS * J + lj0 + e;
+            double wgt = (I != J || bcol < brow) ? 2.0 : ((bcol == brow) ? 1.0 : 0.0);
+            wgt = (gi >= N || gj >= N) ? 0.0 : wgt;
+            const double wij = wgt * (ar * (e ? ac.y : ac.x) - acc[2 * ip + r][j][e]);
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DD; ++k) {
+                const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                r2 = fma(dz, dz, r2);
+            }
+            double m, gf;
+            matern52_fast(r2, m, gf, etab);
+            const double uu = ur * (e ? uc.y : uc.x);
+            const double beta = uu + cb;
+            const double wa = wij * h.amp;
+            const double wam = wa * m;
+            cs.g0 = fma(wam, beta, cs.g0);
+            const double wg = wa * beta * gf;
+#pragma unroll
+            for (int k = 0; k < DD; ++k) {          // dz^2 recomputed: cheaper than keeping it across the Matern chain
+                const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
+                gm[k] = fma(wg * dz, dz, gm[k]);
+            }
+            cs.gg2 = fma(-wam, uu, cs.gg2);
+            cs.gcb = fma(wam, cb, cs.gcb);
+            cs.gtr += (gi == gj) ? wij : 0.0;
+        }
+    }
+}
 template <int DD>
 __device__ __forceinline__ void contract_acc(const double (&acc)[4][2][2], double* gsum_w,
                                              const double* zr_s, const double* zc_s, const double* ur_s,
                                              const double* uc_s, const double* al_r, const double* al_c, int ldz,
                                              const Hyper& h, int N, int family, int I, int J, WarpTile wt,
                                              const double* __restrict__ etab) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int lane = threadIdx.x & 31;
     const bool basis = family == 1;
     const double cb = basis ? h.cb : 1.0;
     double gm[DD];
 #pragma unroll
     for (int k = 0; k < DD; ++k) gm[k] = 0.0;
-    double g0 = 0.0, gg2 = 0.0, gcb = 0.0, gtr = 0.0;
-#pragma unroll 2      // two passes (eight Matern chains) in flight: 267 -> 263 us; four do not fit the register budget
-    for (int q = 0; q < 4; ++q) {
-        const int ip = q >> 1, j = q & 1;
-        const int lj0 = wt.n0 + 8 * j + 2 * t;
-        const int bcol = (wt.n0 >> 3) + j;
-        if (I == J && bcol > (wt.m0 >> 3) + 2 * ip + 1) continue;     // weight 0 on both blocks of this pass
-        double kinv[2][2];
-        switch (q) {                        // static accumulator indices
-        case 0: kinv[0][0] = acc[0][0][0]; kinv[0][1] = acc[0][0][1]; kinv[1][0] = acc[1][0][0]; kinv[1][1] = acc[1][0][1]; break;
-        case 1: kinv[0][0] = acc[0][1][0]; kinv[0][1] = acc[0][1][1]; kinv[1][0] = acc[1][1][0]; kinv[1][1] = acc[1][1][1]; break;
-        case 2: kinv[0][0] = acc[2][0][0]; kinv[0][1] = acc[2][0][1]; kinv[1][0] = acc[3][0][0]; kinv[1][1] = acc[3][0][1]; break;
-        default: kinv[0][0] = acc[2][1][0]; kinv[0][1] = acc[2][1][1]; kinv[1][0] = acc[3][1][0]; kinv[1][1] = acc[3][1][1]; break;
-        }
-        double2 zc[DD];
-#pragma unroll
-        for (int k = 0; k < DD; ++k) zc[k] = *reinterpret_cast<const double2*>(&zc_s[k * ldz + lj0]);
-        const double2 uc = *reinterpret_cast<const double2*>(&uc_s[lj0]);
-        const double2 ac = *reinterpret_cast<const double2*>(&al_c[lj0]);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int li = wt.m0 + 8 * (2 * ip + r) + g;
-            const int gi = TS * I + li;
-            const int brow = li >> 3;
-            double zr[DD];
-#pragma unroll
-            for (int k = 0; k < DD; ++k) zr[k] = zr_s[k * ldz + li];
-            const double ur = basis ? ur_s[li] * h.inv_g2 : 0.0;
-            const double ar = al_r[li];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int gj = TS * J + lj0 + e;
-                double wgt = (I != J || bcol < brow) ? 2.0 : ((bcol == brow) ? 1.0 : 0.0);
-                wgt = (gi >= N || gj >= N) ? 0.0 : wgt;
-                const double wij = wgt * (ar * (e ? ac.y : ac.x) - kinv[r][e]);
-                double r2 = 0.0;
-#pragma unroll
-                for (int k = 0; k < DD; ++k) {
-                    const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
-                    r2 = fma(dz, dz, r2);
-                }
-                double m, gf;
-                matern52_fast(r2, m, gf, etab);
-                const double uu = ur * (e ? uc.y : uc.x);
-                const double beta = uu + cb;
-                const double wa = wij * h.amp;
-                const double wam = wa * m;
-                g0 = fma(wam, beta, g0);
-                const double wg = wa * beta * gf;
-#pragma unroll
-                for (int k = 0; k < DD; ++k) {          // dz^2 recomputed: cheaper than keeping it across the Matern chain
-                    const double dz = zr[k] - (e ? zc[k].y : zc[k].x);
-                    gm[k] = fma(wg * dz, dz, gm[k]);
-                }
-                gg2 = fma(-wam, uu, gg2);
-                gcb = fma(wam, cb, gcb);
-                gtr += (gi == gj) ? wij : 0.0;
-            }
-        }
-    }
-    g0 = warp_sum(g0); gg2 = warp_sum(gg2); gcb = warp_sum(gcb); gtr = warp_sum(gtr);
+    ContractSums cs;
+    cs.g0 = cs.gg2 = cs.gcb = cs.gtr = 0.0;
+    // the pass index is a template parameter (static accumulator registers, see build_pass); two passes (eight Matern
+    // chains) in flight: 267 -> 263 us; four do not fit the register budget
+    contract_pass<DD, 0>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+    contract_pass<DD, 1>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+    __syncwarp();
+    contract_pass<DD, 2>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+    contract_pass<DD, 3>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+    double g0 = warp_sum(cs.g0), gg2 = warp_sum(cs.gg2), gcb = warp_sum(cs.gcb), gtr = warp_sum(cs.gtr);
 #pragma unroll
     for (int k = 0; k < DD; ++k) gm[k] = warp_sum(gm[k]);
     if (lane == 0) {
