@@ -18,6 +18,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -54,6 +55,9 @@ constexpr int DAG_MAX_LOADS = 6;
 // 3 -> 272, 4 -> 275, 6 -> 280: one op (~2 us) covers the L2 / HBM latency of a tile, and a reload hoisted further
 // drags the cross-stream waits of its slot to an earlier op.  N = 2048 does not care (slot availability decides).
 constexpr int DAG_PREFETCH_DEPTH = 1;
+// List scheduling of the bulk stream: tasks that become ready within this many (estimated) microseconds compete with
+// the ready ones (see the scheduling loop).
+constexpr double DAG_LOOKAHEAD_US = 3.0;   // measured at N = 256: 0 -> 256.4 / 132.4 us (ll+grad / ll), 2..4 -> 253.6 / 129.0, 8 -> 255.6 / 131.2
 
 struct DagOp {             // 28 ints, read by every thread of its stream
     int type, I, J, k;
@@ -105,8 +109,23 @@ struct Task {
     bool scheduled = false;
 };
 // estimated costs in microseconds (B200, profiles/r01f_phase_cycles.txt)
-constexpr double C_BUILD = 2.7, C_MMA = 2.3, C_PUT = 0.3, C_TRSM = 3.2, C_P1FIN = 2.7, C_CONTRACT = 3.8,
-                 C_CHAIN = 21.0;
+struct DagCosts { double build, mma, put, trsm, p1fin, contract, chain; };
+inline const DagCosts& dag_costs() {
+    static DagCosts c = [] {
+        DagCosts d{2.7, 2.3, 0.3, 3.2, 2.7, 3.8, 21.0};
+        if (const char* e = getenv("FAB_DAG_COSTS"))          // (development: schedule experiments)
+            sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf,%lf", &d.build, &d.mma, &d.put, &d.trsm, &d.p1fin, &d.contract, &d.chain);
+        return d;
+    }();
+    return c;
+}
+#define C_BUILD (dag_costs().build)
+#define C_MMA (dag_costs().mma)
+#define C_PUT (dag_costs().put)
+#define C_TRSM (dag_costs().trsm)
+#define C_P1FIN (dag_costs().p1fin)
+#define C_CONTRACT (dag_costs().contract)
+#define C_CHAIN (dag_costs().chain)
 
 struct SymOp {            // one op before slot assignment
     int stream;           // 0 bulk, 1 chain
@@ -241,13 +260,15 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
     };
     double tfree[2] = {0.0, 0.0};
     std::vector<int> order[2];
+    double look = DAG_LOOKAHEAD_US;
+    if (const char* e = getenv("FAB_DAG_LOOK")) look = atof(e);          // (development: schedule experiments)
     int remaining = nt;
     while (remaining > 0) {
         int best[2] = {-1, -1};
         double best_est[2] = {1e300, 1e300};
         for (int s = 0; s < 2; ++s) {
             int ready_best = -1, early_best = -1;
-            double early_est = 1e300;
+            double early_est = 1e300, ready_est = 0.0;
             for (int t = 0; t < nt; ++t) {
                 if (T[t].scheduled || (T[t].kind == T_CH) != (s == 1)) continue;
                 double est = tfree[s];
@@ -267,10 +288,14 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
                     const int excess = unsched + (int)ends.size() - (ucap - 1);   // consumers that must finish first
                     if (excess > 0) est = std::max(est, ends[excess - 1] - T[t].cost);
                 }
-                if (est <= tfree[s] + 1e-9) { if (ready_best < 0 || T[t].prio > T[ready_best].prio) ready_best = t; }
+                // a task that becomes ready within `look` us competes with the ready ones: the bulk stream rather idles
+                // for a moment than starts a long low-priority task right before the panel solve the chain waits for
+                if (est <= tfree[s] + (s == 0 ? look : 0.0) + 1e-9) {
+                    if (ready_best < 0 || T[t].prio > T[ready_best].prio) { ready_best = t; ready_est = std::max(est, tfree[s]); }
+                }
                 else if (est < early_est - 1e-9 || (est < early_est + 1e-9 && T[t].prio > T[early_best].prio)) { early_est = est; early_best = t; }
             }
-            if (ready_best >= 0) { best[s] = ready_best; best_est[s] = tfree[s]; }
+            if (ready_best >= 0) { best[s] = ready_best; best_est[s] = ready_est; }
             else if (early_best >= 0) { best[s] = early_best; best_est[s] = early_est; }
         }
         int s;
