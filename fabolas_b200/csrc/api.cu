@@ -939,6 +939,10 @@ extern "C" int fab_debug_trace_read(long long* out) {      // [2][128][4] clock6
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(out, fab::g_trace, sizeof(long long) * 2 * 128 * 4) == cudaSuccess ? 0 : -1;
 }
+extern "C" int fab_debug_trace_w_read(long long* out) {    // [16][128][6] stamps of lane 0 of every bulk warp of CTA 0
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, fab::g_trace_w, sizeof(long long) * 16 * 128 * 6) == cudaSuccess ? 0 : -1;
+}
 extern "C" int fab_debug_program_read(int NT, int nslot, int mode, int* out, int max_ops) {   // (type, I, J, k) per bulk op
     const DagProgram P = build_dag_program(NT, nslot, mode);
     int n = 0;

@@ -156,9 +156,9 @@ __device__ __forceinline__ void matern52_fast(double r2, double& m, double& gfac
 __host__ __device__ constexpr int slice_doubles(int d) { return (d + 1) * TS; }
 
 // Stage the slice of tile-row `I` (observations 64 I .. 64 I + 63) into `buf`; all threads, no barrier.
-__device__ __forceinline__ void stage_slice(double* buf, const GpData& gd, const Hyper& h, int I) {
+__device__ __forceinline__ void stage_slice(double* buf, const GpData& gd, const Hyper& h, int I, int nthr = NTHREADS) {
     const int D = gd.D, d = gd.d;
-    for (int e = threadIdx.x; e < TS * D; e += NTHREADS) {
+    for (int e = threadIdx.x; e < TS * D; e += nthr) {
         const int r = e / D, k = e - r * D;
         const int gi = TS * I + r;
         const double x = (gi < gd.N) ? __ldg(&gd.X[(size_t)gi * D + k]) : 0.0;
@@ -166,7 +166,7 @@ __device__ __forceinline__ void stage_slice(double* buf, const GpData& gd, const
         else buf[d * TS + r] = x;                       // k == d only happens for family 1 (D = d + 1)
     }
     if (gd.family != 1)
-        for (int r = threadIdx.x; r < TS; r += NTHREADS) buf[d * TS + r] = 0.0;
+        for (int r = threadIdx.x; r < TS; r += nthr) buf[d * TS + r] = 0.0;
 }
 
 }  // namespace fab

@@ -18,8 +18,81 @@
 
 namespace fab {
 
-constexpr int DAG_BULK_THREADS = NTHREADS;         // warps 0..7
-constexpr int DAG_THREADS = NTHREADS + 32 * NCW;   // + the chain warps
+// Accumulator layout of the bulk warps (FAB_DAG_LAYOUT, prims.cuh).  A warp issues one DMMA every ~32 cycles whatever
+// else runs on its SM sub-partition (two warps together fill the pipe, one alone gets half of it), so an op lasts as
+// long as its BUSIEST WARP -- and most ops are not full products: panel solves and inverse products have a triangular
+// operand (k-range proportional to the column or to the row of the output block), diagonal tiles need their lower
+// triangle only.  With one 32 x 16 block per warp (round 1) the busiest warp of every such op did the work of a full
+// product (profiles/r02m_fine_trace_layout0.txt: bodies of 0.5 .. 2.1 us side by side, 64 us of arrival spread per
+// evaluation).  Layout 2 gives every warp TWO 16 x 16 units (r, c) and (3 - r, 3 - c) of the 4 x 4 unit grid: the
+// k-ranges of a warp's two units add up to 5/8 of a full product for every triangular operand, whether the range goes
+// with the row or with the column, and a diagonal tile costs its busiest warp 6 of 8 blocks.
+constexpr int DAG_LAYOUT = FAB_DAG_LAYOUT;
+static_assert(DAG_LAYOUT >= 0 && DAG_LAYOUT <= 2, "gp_dag_kernel: accumulator layout 0, 1 or 2");
+constexpr int DAG_NBW = FAB_DAG_NBW;               // bulk warps
+constexpr int DAG_NU = (DAG_LAYOUT == 2) ? 2 : 1;  // accumulator units per warp
+constexpr int DAG_MI = (DAG_LAYOUT == 0) ? 4 : 2;  // 8-row blocks per unit: 32 x 16 or 16 x 16
+constexpr int DAG_RB = TS / (8 * DAG_MI);          // row blocks of units over a tile (2 or 4)
+constexpr int DAG_BULK_THREADS = 32 * DAG_NBW;     // warps 0..DAG_NBW-1
+constexpr int DAG_THREADS = DAG_BULK_THREADS + 32 * NCW;   // + the chain warps
+typedef double DagUnit[DAG_MI][2][2];              // one unit in DMMA accumulator-fragment layout
+struct DagAcc { DagUnit u[DAG_NU]; };
+struct DagTiles { WarpTile u[DAG_NU]; };           // origins of this warp's units inside the 64 x 64 tile
+
+__device__ __forceinline__ DagTiles dag_tiles() {
+    const int w = threadIdx.x >> 5;
+    DagTiles wt;
+    if constexpr (DAG_LAYOUT == 0) {
+        wt.u[0] = warp_tile();
+    } else if constexpr (DAG_LAYOUT == 1) {
+        // 16 warps as 4 x 4 units.  Warps w, w + 4, w + 8, w + 12 share an SM sub-partition s = w & 3: row r = w >> 2
+        // gets column (s - r) & 3, one unit of every row and of every column per sub-partition
+        wt.u[0].m0 = (w >> 2) * 16;
+        wt.u[0].n0 = (((w & 3) - (w >> 2)) & 3) * 16;
+    } else {
+        // warp w = (h, cp, rp): rows {ra, rb} = {0, 3} or {1, 2}, columns {ca, cb} likewise; h = 0: units (ra, ca) and
+        // (rb, cb), h = 1: (ra, cb) and (rb, ca).  Warps w and w + 4 share an SM sub-partition and the 2 x 2 unit set.
+        const int rp = w & 1, cp = (w >> 1) & 1, hh = (w >> 2) & 1;
+        const int ra = rp ? 1 : 0, rb = 3 - ra, ca = cp ? 1 : 0, cb = 3 - ca;
+        wt.u[0].m0 = 16 * ra; wt.u[0].n0 = 16 * (hh ? cb : ca);
+        wt.u[DAG_NU - 1].m0 = 16 * rb; wt.u[DAG_NU - 1].n0 = 16 * (hh ? ca : cb);
+    }
+    return wt;
+}
+__device__ __forceinline__ void dag_acc_zero(DagAcc& acc) {
+#pragma unroll
+    for (int u = 0; u < DAG_NU; ++u) acc_zero(acc.u[u]);
+}
+__device__ __forceinline__ void dag_acc_load(DagAcc& acc, const double* C, const DagTiles& wt) {
+#pragma unroll
+    for (int u = 0; u < DAG_NU; ++u) acc_load(acc.u[u], C, wt.u[u]);
+}
+__device__ __forceinline__ void dag_acc_store(const DagAcc& acc, double* C, const DagTiles& wt) {
+#pragma unroll
+    for (int u = 0; u < DAG_NU; ++u) acc_store(acc.u[u], C, wt.u[u]);
+}
+// acc += sign * opA(A) opB(B) over k in [k_lo, k_hi) per unit; the bounds follow the unit for a triangular operand:
+enum { KR_ZERO = 0, KR_N0 = 1, KR_M0 = 2 };        // k_lo = 0 | n0 | m0
+enum { KR_FULL = 0, KR_N0_END = 1, KR_M0_END = 2 };// k_hi = 64 | n0 + 16 | m0 + rows of the unit
+// lower: only the blocks on and below the block diagonal of the result are needed (diagonal tile)
+template <bool TA, bool TB, bool NEG, int L = DAG_LAYOUT>
+__device__ __forceinline__ void dag_mma(DagAcc& acc, const double* __restrict__ A, const double* __restrict__ B,
+                                        const DagTiles& wt, int lo_sel, int hi_sel, bool lower) {
+#pragma unroll
+    for (int u = 0; u < DAG_NU; ++u) {
+        const WarpTile t = wt.u[u];
+        const int k_lo = lo_sel == KR_ZERO ? 0 : (lo_sel == KR_N0 ? t.n0 : t.m0);
+        const int k_hi = hi_sel == KR_FULL ? TS : (hi_sel == KR_N0_END ? t.n0 + 16 : t.m0 + 8 * DAG_MI);
+        if (!lower) {
+            tile_mma<TA, TB, NEG, DAG_MI, 2>(acc.u[u], A, B, t, k_lo, k_hi);
+        } else if constexpr (L == 0) {
+            tile_mma_lower<TA, TB, NEG>(acc.u[u], A, B, t, k_lo);       // (k_hi == 64 for every lower product)
+        } else {
+            if (t.n0 < t.m0) tile_mma<TA, TB, NEG, DAG_MI, 2>(acc.u[u], A, B, t, k_lo, k_hi);
+            else if (t.n0 == t.m0) tile_mma<TA, TB, NEG, DAG_MI, 2, TS, TS, true>(acc.u[u], A, B, t, k_lo, k_hi);
+        }
+    }
+}
 
 // Peer exchange of the per-walker results (multi-GPU likelihood step): instead of an
 // all-gather after the kernel, every CTA stores its walker's result row [grad (Pk+1) | ll | info] straight into the
@@ -62,7 +135,7 @@ struct DagArgs {
 
 __host__ __device__ inline size_t dag_smem_bytes(int nslot, int d, int resident_np) {
     const size_t coords = resident_np ? (size_t)(d + 4) * resident_np : (size_t)(2 * (d + 1) * TS + 2 * TS);
-    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + EXP_TAB_N + 512 + 128 + 64 + 64 + 64 + 4 * TS) + 8 * coords +
+    return (size_t)nslot * TILE_BYTES + 8 * (size_t)(512 + EXP_TAB_N + 512 + 256 + 64 + 64 + 64 + 4 * TS) + 8 * coords +
            8 * MAX_SLOTS + 64 + 512;       // mbarriers, stream counters, op-record ring (4 x 112 B)
 }
 
@@ -95,7 +168,7 @@ __device__ __forceinline__ void spin_until(int* p, int target) {
 // parameter: with a run-time pass loop the accumulator registers could only be addressed through a switch, and 40 %
 // of the 439 instructions of a pass were register moves and selects (the ops are issue-bound, not FP64-bound).
 template <int DD, int Q>
-__device__ __forceinline__ void build_pass(double (&acc)[4][2][2], const double* zr_s, const double* zc_s,
+__device__ __forceinline__ void build_pass(DagUnit& acc, const double* zr_s, const double* zc_s,
                                            const double* ur_s, const double* uc_s, int ldz, const Hyper& h, int N,
                                            bool basis, double cb, int I, int J, WarpTile wt, const double* __restrict__ etab) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -137,16 +210,29 @@ __device__ __forceinline__ void build_pass(double (&acc)[4][2][2], const double*
     }
 }
 template <int DD>
-__device__ __forceinline__ void build_acc(double (&acc)[4][2][2], const double* zr_s, const double* zc_s,
+__device__ __forceinline__ void build_acc(DagUnit& acc, const double* zr_s, const double* zc_s,
                                           const double* ur_s, const double* uc_s, int ldz, const Hyper& h, int N,
                                           int family, int I, int J, WarpTile wt, const double* __restrict__ etab) {
     const bool basis = family == 1;
     const double cb = basis ? h.cb : 1.0;
     // (the warp barriers keep the compiler from overlapping the passes, which costs registers and gained nothing)
     build_pass<DD, 0>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab); __syncwarp();
-    build_pass<DD, 1>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab); __syncwarp();
-    build_pass<DD, 2>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab); __syncwarp();
-    build_pass<DD, 3>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab);
+    build_pass<DD, 1>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab);
+    if constexpr (DAG_MI == 4) {
+        __syncwarp();
+        build_pass<DD, 2>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab); __syncwarp();
+        build_pass<DD, 3>(acc, zr_s, zc_s, ur_s, uc_s, ldz, h, N, basis, cb, I, J, wt, etab);
+    }
+}
+template <int DD>
+__device__ __forceinline__ void dag_build(DagAcc& acc, const double* zr_s, const double* zc_s, const double* ur_s,
+                                          const double* uc_s, int ldz, const Hyper& h, int N, int family, int I, int J,
+                                          const DagTiles& wt, const double* __restrict__ etab) {
+#pragma unroll
+    for (int u = 0; u < DAG_NU; ++u) {
+        if (u) __syncwarp();
+        build_acc<DD>(acc.u[u], zr_s, zc_s, ur_s, uc_s, ldz, h, N, family, I, J, wt.u[u], etab);
+    }
 }
 
 // Contract one 64x64 tile of (alpha alpha^T - K^-1), held in this warp's DMMA accumulator fragment, with
@@ -158,7 +244,7 @@ struct ContractSums {            // per-thread partial sums of one contraction
     double g0, gg2, gcb, gtr;
 };
 template <int DD, int Q>
-__device__ __forceinline__ void contract_pass(const double (&acc)[4][2][2], ContractSums& cs, double (&gm)[DD],
+__device__ __forceinline__ void contract_pass(const DagUnit& acc, ContractSums& cs, double (&gm)[DD],
                                               const double* zr_s, const double* zc_s, const double* ur_s,
                                               const double* uc_s, const double* al_r, const double* al_c, int ldz,
                                               const Hyper& h, int N, bool basis, double cb, int I, int J, WarpTile wt,
@@ -215,10 +301,10 @@ __device__ __forceinline__ void contract_pass(const double (&acc)[4][2][2], Cont
     }
 }
 template <int DD>
-__device__ __forceinline__ void contract_acc(const double (&acc)[4][2][2], double* gsum_w,
+__device__ __forceinline__ void contract_acc(const DagAcc& acc, double* gsum_w,
                                              const double* zr_s, const double* zc_s, const double* ur_s,
                                              const double* uc_s, const double* al_r, const double* al_c, int ldz,
-                                             const Hyper& h, int N, int family, int I, int J, WarpTile wt,
+                                             const Hyper& h, int N, int family, int I, int J, const DagTiles& wts,
                                              const double* __restrict__ etab) {
     const int lane = threadIdx.x & 31;
     const bool basis = family == 1;
@@ -230,11 +316,18 @@ __device__ __forceinline__ void contract_acc(const double (&acc)[4][2][2], doubl
     cs.g0 = cs.gg2 = cs.gcb = cs.gtr = 0.0;
     // the pass index is a template parameter (static accumulator registers, see build_pass); two passes (eight Matern
     // chains) in flight: 267 -> 263 us; four do not fit the register budget
-    contract_pass<DD, 0>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
-    contract_pass<DD, 1>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
-    __syncwarp();
-    contract_pass<DD, 2>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
-    contract_pass<DD, 3>(acc, cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+#pragma unroll
+    for (int u = 0; u < DAG_NU; ++u) {
+        const WarpTile wt = wts.u[u];
+        if (u) __syncwarp();
+        contract_pass<DD, 0>(acc.u[u], cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+        contract_pass<DD, 1>(acc.u[u], cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+        if constexpr (DAG_MI == 4) {
+            __syncwarp();
+            contract_pass<DD, 2>(acc.u[u], cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+            contract_pass<DD, 3>(acc.u[u], cs, gm, zr_s, zc_s, ur_s, uc_s, al_r, al_c, ldz, h, N, basis, cb, I, J, wt, etab);
+        }
+    }
     double g0 = warp_sum(cs.g0), gg2 = warp_sum(cs.gg2), gcb = warp_sum(cs.gcb), gtr = warp_sum(cs.gtr);
 #pragma unroll
     for (int k = 0; k < DD; ++k) gm[k] = warp_sum(gm[k]);
@@ -265,8 +358,8 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     double* dinv = slots + (size_t)a.nslot * TILE_ELEMS;      // 512: 8x8 inverses of the tile the chain works on
     double* etab = dinv + 512;                                // exp table
     double* part = etab + EXP_TAB_N;                          // 512: partial sums of the bulk matvec epilogues
-    double* red = part + 512;                                 // 128: final reductions
-    double* crhs = red + 128;                                 // 64: chain right-hand side
+    double* red = part + 512;                                 // 256: final reductions (16 warps x 12)
+    double* crhs = red + 256;                                 // 64: chain right-hand side
     double* cz = crhs + 64;                                   // 64: chain z_K
     double* rinv = cz + 64;                                   // 64: reciprocal pivots, 8 per 8-column step
     double* cpart = rinv + 64;                                // 256: partial sums across the chain warps
@@ -325,9 +418,9 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     if (ring_lane) cp_async_wait<2>();    // op record 0 has landed; the barrier publishes it
     __syncthreads();                      // the only block-wide barrier of an evaluation: the two streams part here
 
-    if (w >= NWARPS) {
+    if (w >= DAG_NBW) {
         // ======================================= CHAIN stream =======================================
-        const int cw = w - NWARPS;
+        const int cw = w - DAG_NBW;
         double logdet = 0.0, zz = 0.0;
         int first_fail = 0;                   // (warp 0, lane 0)
         PHBC(55);
@@ -337,7 +430,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             PHBC(56);
             TRC(j, 0);
             if (wo > 0) {
-                if (lane == 0) spin_until(&sync[0], NWARPS * wo);
+                if (lane == 0) spin_until(&sync[0], DAG_NBW * wo);
                 __syncwarp();
             }
             PHEC(56);
@@ -415,10 +508,10 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     }
 
     // ========================================= BULK stream =========================================
-    const WarpTile wt = warp_tile();
+    const DagTiles wt = dag_tiles();
     const int g = lane >> 2, t = lane & 3;
-    double acc[4][2][2];
-    acc_zero(acc);
+    DagAcc acc;
+    dag_acc_zero(acc);
     double* gsum_w = red + w * (MAX_PK + 1);   // this warp's gradient partial sums (contract_acc)
     if (lane <= MAX_PK) gsum_w[lane] = 0.0;
     int cur_r = -1, cur_c = -1;           // tile rows whose coordinate slices are staged (slice mode)
@@ -427,6 +520,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     for (int i = 0; i < a.nbulk; ++i) {
         PHB(41);
         TRB(i, 0);
+        TRW(i, 0);
         const int* rec = ring + (i & 3) * 28;         // published by the previous barrier
         const int type = rec[0], I = rec[1], J = rec[2], k = rec[3];
         const int sA = rec[4], sB = rec[5], sC = rec[6];
@@ -434,6 +528,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         if (tid == 0 && (flags & DOPF_WAIT_READ)) bulk_s2g_wait_read();
         if (ring_lane) cp_async_wait<1>();            // record i + 1 has landed (i + 2 may still be in flight)
         named_bar_sync(1, DAG_BULK_THREADS);          // every bulk warp is done with the previous operation
+        TRW(i, 1);
         ring_fetch(i + 3);                            // into the slot of record i - 1
         if (wo > 0) {
             // chain op c publishes two events: 2c + 1 (tiles final) and 2c + 2 (vectors); a panel solve that only
@@ -446,6 +541,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             if (lane == 0) spin_until(&sync[1], need);
             __syncwarp();
         }
+        TRW(i, 2);
         if (tid == 0) {
             const int nload = rec[12];
             if (flags & DOPF_DRAIN) bulk_s2g_wait_all();
@@ -457,6 +553,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             if (st_slot >= 0)
                 bulk_s2g(ws_tile(st_tile), slots + (size_t)st_slot * TILE_ELEMS, TILE_BYTES);
         }
+        TRW(i, 3);
         PHE(41);
         PHB(42);
         for (int s = 0; s < MAX_SLOTS; ++s)
@@ -467,6 +564,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         PHE(42);
         PHB(42 + type);
         TRB(i, 1);
+        TRW(i, 4);
         const double* A = slots + (size_t)(sA < 0 ? 0 : sA) * TILE_ELEMS;
         const double* Bt = slots + (size_t)(sB < 0 ? 0 : sB) * TILE_ELEMS;
         double* C = slots + (size_t)(sC < 0 ? 0 : sC) * TILE_ELEMS;
@@ -474,8 +572,8 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         if (type == DOP_BUILD || (type == DOP_P2_MMA && (flags & DOPF_LAST))) {
             if (!a.resident) {            // slice mode: stage the coordinates (and alpha) of the two tile rows
                 bool staged = false;
-                if (cur_r != I) { stage_slice(sl_r, gd, hfull, I); cur_r = I; staged = true; }
-                if (cur_c != J) { stage_slice(sl_c, gd, hfull, J); cur_c = J; staged = true; }
+                if (cur_r != I) { stage_slice(sl_r, gd, hfull, I, DAG_BULK_THREADS); cur_r = I; staged = true; }
+                if (cur_c != J) { stage_slice(sl_c, gd, hfull, J, DAG_BULK_THREADS); cur_c = J; staged = true; }
                 if (type == DOP_P2_MMA) {
                     if (tid < TS) al_r[tid] = alv[TS * I + tid];
                     else if (tid < 2 * TS) al_c[tid - TS] = alv[TS * J + tid - TS];
@@ -490,86 +588,100 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         const double* uc_p = a.resident ? us_all + TS * J : sl_c + d * TS;
         const int ldz = a.resident ? Np : TS;
 
-        if (flags & DOPF_GET_BEFORE) acc_load(acc, C, wt);      // partial tile P(I,J) continues in the accumulators
+        if (flags & DOPF_GET_BEFORE) dag_acc_load(acc, C, wt);  // partial tile P(I,J) continues in the accumulators
+#ifdef FAB_EXP_TWICE          // experiment: every op body twice (same instructions: second run = warm instruction caches)
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep) {
+#endif
         switch (type) {
         case DOP_BUILD: {
-            build_acc<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab);
+            dag_build<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab);
             break;
         }
         case DOP_MMA_NT:
-            if (I != J) tile_mma<false, true, true>(acc, A, Bt, wt, 0, TS);
-            else tile_mma_lower<false, true, true>(acc, A, Bt, wt, 0);
+            dag_mma<false, true, true>(acc, A, Bt, wt, KR_ZERO, KR_FULL, I == J);
             break;
         case DOP_PUT:
-            acc_store(acc, C, wt);
+            dag_acc_store(acc, C, wt);
             fence_proxy_async();
             break;
         case DOP_GET:
-            acc_load(acc, C, wt);
+            dag_acc_load(acc, C, wt);
             break;
         case DOP_TRSM: {
             // L(I,J) = U(I,J) W(J,J)^T in place (W lower triangular: k <= n), then accw_I += L(I,J) z_J
-            double r2[4][2][2];
-            acc_zero(r2);
-            tile_mma<false, true, false>(r2, C, Bt, wt, 0, wt.n0 + 16);
+            DagAcc r2;
+            dag_acc_zero(r2);
+            dag_mma<false, true, false>(r2, C, Bt, wt, KR_ZERO, KR_N0_END, false);
             if (lane == 0) spin_until(&sync[1], 2 * J + 2);
             __syncwarp();
             const double* zJ = zv + TS * J;
-            double zc0[2], zc1[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { zc0[j] = zJ[wt.n0 + 8 * j + 2 * t]; zc1[j] = zJ[wt.n0 + 8 * j + 2 * t + 1]; }
+            for (int u = 0; u < DAG_NU; ++u) {
+                const int m0 = wt.u[u].m0, n0 = wt.u[u].n0;
+                double zc0[2], zc1[2];
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-                double s = 0.0;
+                for (int j = 0; j < 2; ++j) { zc0[j] = zJ[n0 + 8 * j + 2 * t]; zc1[j] = zJ[n0 + 8 * j + 2 * t + 1]; }
 #pragma unroll
-                for (int j = 0; j < 2; ++j) s = fma(r2[i4][j][0], zc0[j], fma(r2[i4][j][1], zc1[j], s));
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (t == 0) part[(wt.n0 >> 4) * TS + wt.m0 + 8 * i4 + g] = s;
+                for (int i4 = 0; i4 < DAG_MI; ++i4) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) s = fma(r2.u[u][i4][j][0], zc0[j], fma(r2.u[u][i4][j][1], zc1[j], s));
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (t == 0) part[(n0 >> 4) * TS + m0 + 8 * i4 + g] = s;
+                }
             }
             named_bar_sync(1, DAG_BULK_THREADS);       // every warp has read its rows of U
-            acc_store(r2, C, wt);
+            dag_acc_store(r2, C, wt);
             fence_proxy_async();
             if (tid < TS) accw[TS * I + tid] += (part[tid] + part[TS + tid]) + (part[2 * TS + tid] + part[3 * TS + tid]);
             break;
         }
         case DOP_P1_MMA:
-            if (flags & DOPF_FIRST) acc_zero(acc);
+            if (flags & DOPF_FIRST) dag_acc_zero(acc);
             // W(J,J) is lower triangular: rows k' < n contribute nothing
-            tile_mma<false, false, false>(acc, A, Bt, wt, (k == J) ? wt.n0 : 0, TS);
+            dag_mma<false, false, false>(acc, A, Bt, wt, (k == J) ? KR_N0 : KR_ZERO, KR_FULL, false);
             break;
         case DOP_P1_FIN: {
             // W(I,J) = -W(I,I) T(I,J) in place  (W(I,I) lower triangular: k <= m), then alpha_J += W(I,J)^T z_I
-            double r2[4][2][2];
-            acc_zero(r2);
-            tile_mma<false, false, true>(r2, A, C, wt, 0, wt.m0 + 32);
+            DagAcc r2;
+            dag_acc_zero(r2);
+            dag_mma<false, false, true>(r2, A, C, wt, KR_ZERO, KR_M0_END, false);
             const double* zI = zv + TS * I;
-            double zr4[4];
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) zr4[i4] = zI[wt.m0 + 8 * i4 + g];
+            for (int u = 0; u < DAG_NU; ++u) {
+                const int m0 = wt.u[u].m0, n0 = wt.u[u].n0;
+                double zr4[DAG_MI];
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+                for (int i4 = 0; i4 < DAG_MI; ++i4) zr4[i4] = zI[m0 + 8 * i4 + g];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    double s = 0.0;
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) s = fma(r2[i4][j][e], zr4[i4], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    s += __shfl_xor_sync(0xffffffffu, s, 8);
-                    s += __shfl_xor_sync(0xffffffffu, s, 16);
-                    if (g == 0) part[(wt.m0 >> 5) * TS + wt.n0 + 8 * j + 2 * t + e] = s;
-                }
+                    for (int e = 0; e < 2; ++e) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int i4 = 0; i4 < DAG_MI; ++i4) s = fma(r2.u[u][i4][j][e], zr4[i4], s);
+                        s += __shfl_xor_sync(0xffffffffu, s, 4);
+                        s += __shfl_xor_sync(0xffffffffu, s, 8);
+                        s += __shfl_xor_sync(0xffffffffu, s, 16);
+                        if (g == 0) part[(m0 / (8 * DAG_MI)) * TS + n0 + 8 * j + 2 * t + e] = s;
+                    }
+            }
             named_bar_sync(1, DAG_BULK_THREADS);       // every warp has read its columns of the product
-            acc_store(r2, C, wt);
+            dag_acc_store(r2, C, wt);
             fence_proxy_async();
-            if (tid < TS) alv[TS * J + tid] += part[tid] + part[TS + tid];
+            if (tid < TS) {
+                double s = part[tid] + part[TS + tid];
+                if (DAG_RB == 4) s += part[2 * TS + tid] + part[3 * TS + tid];
+                alv[TS * J + tid] += s;
+            }
             break;
         }
         case DOP_P2_MMA:
-            if (flags & DOPF_FIRST) acc_zero(acc);
+            if (flags & DOPF_FIRST) dag_acc_zero(acc);
             // W(I,I) is lower triangular: (W_II)[k'][m] = 0 for k' < m
-            if (I != J) tile_mma<true, false, false>(acc, A, Bt, wt, (k == I) ? wt.m0 : 0, TS);
-            else tile_mma_lower<true, false, false>(acc, A, Bt, wt, (k == I) ? wt.m0 : 0);
+            dag_mma<true, false, false>(acc, A, Bt, wt, (k == I) ? KR_M0 : KR_ZERO, KR_FULL, I == J);
             if (flags & DOPF_LAST) {
                 PHB(50);
                 const double* ar_p = a.resident ? alv + TS * I : al_r;
@@ -580,13 +692,18 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             break;
         default: break;
         }
+#ifdef FAB_EXP_TWICE
+        if (rep == 0) TRB(i, 3);
+        }
+#endif
         if (flags & DOPF_PUT_AFTER) {         // the tile leaves the accumulators: slot C is no operand of this op ...
             if (flags & DOPF_PUT_BARRIER) named_bar_sync(1, DAG_BULK_THREADS);     // ... or everybody is done reading it
-            acc_store(acc, C, wt);
+            dag_acc_store(acc, C, wt);
             fence_proxy_async();
         }
         PHE(42 + type);
         TRB(i, 2);
+        TRW(i, 5);
         __syncwarp();
         if (lane == 0) sync_arrive(&sync[0]);
     }
@@ -603,7 +720,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             double gacc[MAX_PK + 1];
             for (int q = 0; q <= MAX_PK; ++q) {
                 double sgm = 0.0;
-                for (int ww = 0; ww < NWARPS; ++ww) sgm += red[ww * (MAX_PK + 1) + q];
+                for (int ww = 0; ww < DAG_NBW; ++ww) sgm += red[ww * (MAX_PK + 1) + q];
                 gacc[q] = sgm;
             }
             double* go = a.grad + (size_t)b * (Pk + 1);
@@ -662,7 +779,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     PHE(40);
 }
 
-// 12 warps: 65536 / 384 = 170 -> 168 registers per thread.
+// 12 warps: 65536 / 384 = 170 -> 168 registers per thread; 20 warps: 65536 / 640 = 102 -> 96.
 #define FAB_DAG_KERNEL_ATTR __global__ void __launch_bounds__(DAG_THREADS, 1)
 // One instantiation per number of Matern axes d = gd.d (1..MAX_D): the covariance generation and the contraction are
 // unrolled over d, and a kernel that carried all eight versions was 406 KB of code (the sampler 921 KB) -- far more
@@ -674,7 +791,10 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     dag_eval<DD>(a, blockIdx.x, smem_raw, phases, true);
 }
 
-// host side: run `...` with `constexpr int DD = d`
+// host side: run `...` with `constexpr int DD = d`  (development builds: -DFAB_DEV_D=5 instantiates one d only)
+#ifdef FAB_DEV_D
+#define FAB_DISPATCH_D(d, ...) { constexpr int DD = FAB_DEV_D; __VA_ARGS__; }
+#else
 #define FAB_DISPATCH_D(d, ...)                                   \
     switch (d) {                                                 \
     case 1: { constexpr int DD = 1; __VA_ARGS__; } break;        \
@@ -686,5 +806,6 @@ FAB_DAG_KERNEL_ATTR gp_dag_kernel(DagArgs a) {
     case 7: { constexpr int DD = 7; __VA_ARGS__; } break;        \
     default: { constexpr int DD = 8; __VA_ARGS__; } break;       \
     }
+#endif
 
 }  // namespace fab

@@ -24,15 +24,23 @@ namespace fab {
 
 // Optional per-phase cycle counters (development builds only: -DFAB_PHASE_PROF, tools/phase_prof.py).
 // Thread 0 of CTA 0 brackets a region with PHB(id) / PHE(id); both are fire-and-forget reductions.
+// Accumulator layout of the bulk warps of gp_dag_kernel (gp_dag.cuh): 2 = eight warps, two paired 16 x 16 units each
+// (shipped); 0 = eight warps, one 32 x 16 block each (round 1); 1 = sixteen warps, one 16 x 16 unit each (experiment)
+#ifndef FAB_DAG_LAYOUT
+#define FAB_DAG_LAYOUT 2
+#endif
+#define FAB_DAG_NBW (FAB_DAG_LAYOUT == 1 ? 16 : 8)
 #if defined(FAB_PHASE_PROF) && !defined(FAB_CUSIM)
 __device__ long long g_phase[64];
 #define PHB(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
 #define PHE(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
 __device__ long long g_trace[2][128][4];
 #define TRB(i, k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && (i) < 128) g_trace[0][i][k] = clock64(); } while (0)
-#define TRC(i, k) do { if (threadIdx.x == 256 && blockIdx.x == 0 && (i) < 128) g_trace[1][i][k] = clock64(); } while (0)
-#define PHBC(id) do { if (threadIdx.x == 256 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
-#define PHEC(id) do { if (threadIdx.x == 256 && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
+__device__ long long g_trace_w[16][128][6];     // per bulk warp (lane 0): arrive, barrier, chain wait, TMA issued, loads landed, end
+#define TRW(i, k) do { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0 && (i) < 128) g_trace_w[threadIdx.x >> 5][i][k] = clock64(); } while (0)
+#define TRC(i, k) do { if (threadIdx.x == 32 * FAB_DAG_NBW && blockIdx.x == 0 && (i) < 128) g_trace[1][i][k] = clock64(); } while (0)
+#define PHBC(id) do { if (threadIdx.x == 32 * FAB_DAG_NBW && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)(-clock64())); } while (0)
+#define PHEC(id) do { if (threadIdx.x == 32 * FAB_DAG_NBW && blockIdx.x == 0) atomicAdd((unsigned long long*)&g_phase[id], (unsigned long long)clock64()); } while (0)
 #else
 #define PHB(id) do {} while (0)
 #define PHE(id) do {} while (0)
@@ -40,6 +48,7 @@ __device__ long long g_trace[2][128][4];
 #define PHEC(id) do {} while (0)
 #define TRB(i, k) do {} while (0)
 #define TRC(i, k) do {} while (0)
+#define TRW(i, k) do {} while (0)
 #endif
 
 constexpr double kTiny = 1.25e-12;        // george's default white noise (oracle/george_oracle.py TINY)

@@ -92,7 +92,8 @@ __device__ __forceinline__ void acc_store(const double (&acc)[MI][NJ][2], double
 
 // acc += sign * opA(A) * opB(B) restricted to k in [k_lo, k_hi) (multiples of 4).
 //   opA(A)[m][k] = TA ? A[k][m] : A[m][k]        opB(B)[k][n] = TB ? B[n][k] : B[k][n]
-template <bool TA, bool TB, bool NEG, int MI = 4, int NJ = 2, int LDA = TS, int LDB = TS>
+// SKIP01: the block (i, j) = (0, 1) is left alone (a 16 x 16 unit on the diagonal of a lower-triangular result).
+template <bool TA, bool TB, bool NEG, int MI = 4, int NJ = 2, int LDA = TS, int LDB = TS, bool SKIP01 = false>
 __device__ __forceinline__ void tile_mma(double (&acc)[MI][NJ][2], const double* __restrict__ A,
                                          const double* __restrict__ B, WarpTile wt, int k_lo, int k_hi) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -118,7 +119,8 @@ __device__ __forceinline__ void tile_mma(double (&acc)[MI][NJ][2], const double*
 #pragma unroll
         for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < NJ; ++j)
+                if (!(SKIP01 && i == 0 && j == 1)) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 
