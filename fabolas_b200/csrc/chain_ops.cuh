@@ -11,6 +11,9 @@
 
 namespace fab {
 
+#ifndef CHT
+#define CHT(jb, k) do {} while (0)        // (tools/microbench/potrf64_bench.cu: clock stamps of warp 0)
+#endif
 constexpr int NCW = 4;                 // chain warps (one per SM sub-partition)
 __device__ __forceinline__ void chain_bar() { named_bar_sync(2, 32 * NCW); }
 
@@ -112,6 +115,7 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
             const int o = 8 * jb;
             double* rv = rinv + 8 * jb;
             PHBC(60);
+            CHT(jb, 0);
             if (lane == 0) {
                 const int f = potrf8(A, jb, rv);
                 if (f && *failp == 0) *failp = f;
@@ -119,10 +123,13 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
             __syncwarp();
             PHEC(60);
             PHBC(61);
+            CHT(jb, 1);
             if (jb >= 1) named_bar_sync(4, NT128);          // the workers have applied step jb - 1 to the rest of the tile
+            CHT(jb, 2);
             if (jb + 1 < nb) {
                 if (lane < 8) solve_row8(A, o + 8 + lane, o, rv);
                 __syncwarp();
+                CHT(jb, 4);
                 double c0, c1;
                 blk_load(c0, c1, A, jb + 1, jb + 1);
 #pragma unroll
@@ -133,6 +140,7 @@ __device__ __forceinline__ void potrf64_chain(double* A, double* W, double* dinv
                 blk_store(c0, c1, A, jb + 1, jb + 1);
                 __syncwarp();
             }
+            CHT(jb, 3);
             named_bar_arrive(3, NT128);
             PHEC(61);
         }

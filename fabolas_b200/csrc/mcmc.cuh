@@ -196,6 +196,7 @@ __device__ __forceinline__ double mcmc_log_prob(const McmcArgs& m, unsigned char
                                                 int* flag) {
     const int cta = blockIdx.x;
     double prior_lp = 0.0;
+    PHB(33);
     if (threadIdx.x == 0) {
         prior_lp = mcmc_log_prior(m.prior, m.q + (size_t)cta * m.P, m.P, m.dag.gd.d,
                                   const_cast<double*>(m.dag.theta) + (size_t)cta * m.dag.gd.Pk,
@@ -203,12 +204,15 @@ __device__ __forceinline__ double mcmc_log_prob(const McmcArgs& m, unsigned char
         *flag = prior_lp > -INFINITY ? 1 : 0;     // NaN cannot occur: every term is finite inside the box (+inf at noise == 0)
     }
     __syncthreads();
+    PHE(33);
     const bool run = *flag != 0;                  // uniform over the CTA
+    PHB(34);
     if (run) {
         dag_eval<DD>(m.dag, cta, smem_raw, phases, first);
         first = false;
     }
     __syncthreads();
+    PHE(34);
     if (threadIdx.x == 0) {
         if (!run) return -INFINITY;
         const double ll = m.dag.ll[cta];
@@ -237,10 +241,12 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
     // One loop over "rounds" so that the evaluation (the bulk of the code) is instantiated ONCE: round -1 computes the
     // log-probability of the initial positions (emcee: state.log_prob = compute_log_prob(coords) when not given),
     // rounds 2 * step + split are the half-steps.
+    PHB(30);
     for (int round = m.init_lp ? -1 : 0; round < 2 * m.nsteps; ++round) {
         const bool init = round < 0;
         const int step = init ? 0 : round >> 1, split = init ? 0 : round & 1;
         const long long iter = m.iter0 + step;
+        PHB(31);
         if (!init && split == 0) {
             // ---- split of this step: rank the K keys; order[r] = walker of rank r ----
             for (int i = tid; i < K; i += DAG_THREADS)
@@ -254,8 +260,10 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
             }
             __syncthreads();
         }
+        PHE(31);
         const int items = init ? K : half;
         for (int mm = cta * W + R; mm < items; mm += gridDim.x * W) {
+            PHB(32);
             const int s = init ? mm : order[split * half + mm];
             double zfac = 0.0;
             if (init) {
@@ -274,7 +282,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
                 zfac = (P - 1.0) * log(zz);
             }
             __syncthreads();
+            PHE(32);
             const double new_lp = mcmc_log_prob<DD>(m, smem_raw, phases, first, flag);
+            PHB(35);
             if (tid == 0 && init) {
                 if (m.world > 1) { for (int r = 0; r < W; ++r) m.peer_lp[r][s] = new_lp; }
                 else m.lp[s] = new_lp;
@@ -310,9 +320,13 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
                     }
                 }
             }
+            PHE(35);
         }
+        PHB(36);
         box_barrier(m, gen, xgen);
+        PHE(36);
     }
+    PHE(30);
 }
 
 // Log-priors (and the theta / yerr2 they decode to) for K rows: the test hook that pins the device prior
