@@ -124,6 +124,46 @@ __device__ __forceinline__ void tile_mma(double (&acc)[MI][NJ][2], const double*
     }
 }
 
+// Two 16 x 16 units of one warp (origins w0, w1) over the same k-range in ONE loop: eight independent DMMA chains in
+// flight instead of four after four (gp_dag.cuh, accumulator layout 2: full products).
+template <bool TA, bool TB, bool NEG>
+__device__ __forceinline__ void tile_mma_pair(double (&acc0)[2][2][2], double (&acc1)[2][2][2], const double* __restrict__ A,
+                                              const double* __restrict__ B, WarpTile w0, WarpTile w1, int k_lo, int k_hi) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int sg = (g & 3) << 2, st = t << 2;
+    int a_off[2][2], b_off[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const WarpTile wt = u ? w1 : w0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a_off[u][i] = TA ? (t * TS + ((wt.m0 + 8 * i + g) ^ st)) : ((wt.m0 + 8 * i + g) * TS + t);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) b_off[u][j] = TB ? ((wt.n0 + 8 * j + g) * TS + t) : (t * TS + ((wt.n0 + 8 * j + g) ^ st));
+    }
+#pragma unroll 4
+    for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
+        const int krow = k0 ^ sg;
+        double a[2][2], b[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double v = A[a_off[u][i] + (TA ? k0 * TS : krow)];
+                a[u][i] = NEG ? -v : v;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[u][j] = B[b_off[u][j] + (TB ? krow : k0 * TS)];
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                dmma(acc0[i][j][0], acc0[i][j][1], a[0][i], b[0][j]);
+                dmma(acc1[i][j][0], acc1[i][j][1], a[1][i], b[1][j]);
+            }
+    }
+}
+
 // The same product when only the blocks on and below the block diagonal of the 64 x 64 result are needed (a
 // diagonal tile of the covariance update or of K^-1): a warp whose 32 x 16 block lies above the diagonal does
 // nothing, one whose upper 16 rows do computes the lower 16 only (8-row granularity of the decision: rows

@@ -8,6 +8,7 @@ from fabolas_b200 import Engine
 from fabolas_b200.workloads import gp_workload
 libs = [a for a in sys.argv[1:] if a.endswith(".so")]
 cfgs = [int(a) for a in sys.argv[1:] if a.isdigit()] or [2]
+WALKERS = {5: 128}      # N = 2048: one wave
 def timeit(f, n=30):
     for _ in range(5): f()
     torch.cuda.synchronize()
@@ -19,7 +20,7 @@ def timeit(f, n=30):
     ts.sort()
     return ts[len(ts) // 2]
 for cfg in cfgs:
-    w = gp_workload(cfg)
+    w = gp_workload(cfg, n_walkers=WALKERS.get(cfg))
     ref = None
     for name in libs:
         eng = Engine(device="cuda:0", lib_path=os.path.join(ROOT, "fabolas_b200", "_lib", name))
@@ -27,8 +28,8 @@ for cfg in cfgs:
         th, ye = eng.tensor(w["theta"]), eng.tensor(w["yerr2"])
         out = eng.loglik(th, ye, grad=True)
         ll, g = out[0].cpu().numpy().copy(), out[1].cpu().numpy().copy()
-        tg = timeit(lambda: eng.loglik(th, ye, grad=True))
-        tl = timeit(lambda: eng.loglik(th, ye, grad=False))
+        tg = timeit(lambda: eng.loglik(th, ye, grad=True), 30 if cfg != 5 else 5)
+        tl = timeit(lambda: eng.loglik(th, ye, grad=False), 30 if cfg != 5 else 5)
         msg = f"config {cfg} {name}: ll+grad {tg:.1f} us, ll {tl:.1f} us"
         if ref is None:
             ref = (ll, g)
