@@ -48,7 +48,10 @@ enum DagOpFlags {
     // PUT and GET do not run as ops of their own: they ride on the op that produces / continues the accumulators
     DOPF_GET_BEFORE = 32, // acc = slot C (partial tile P(I,J)) before the op's own work
     DOPF_PUT_AFTER = 64,  // slot C = acc after the op's own work; put_kind = kind of the tile (U, P or T)
-    DOPF_PUT_BARRIER = 128 // slot C is an operand slot of this very op (no other slot was free): the bulk warps meet first
+    DOPF_PUT_BARRIER = 128,// slot C is an operand slot of this very op (no other slot was free): the bulk warps meet first
+    // A covariance tile followed by its first update is ONE op: the tile is generated into the accumulators while the
+    // operand tiles of the update are still on their way (one op start less per tile, the TMA latency hidden)
+    DOPF_BUILD_FIRST = 256
 };
 constexpr int DAG_MAX_LOADS = 6;
 // A reload is issued at most this many ops ahead of its consumer.  Measured (N = 256, ll+grad): 1 -> 267 us, 2 -> 270,
@@ -312,6 +315,7 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
 
     // ---- expand into symbolic ops with estimated start times ----
     std::vector<SymOp> ops;
+    const bool fuse_build = getenv("FAB_DAG_NOFUSE") == nullptr;      // (development: A/B of the fused BUILD + MMA op)
     int pending_get = -1;                      // partial tile a GET wants: rides on the next op pushed
     double pending_get_t = 0.0;
     auto push = [&](int stream, int type, int I, int J, int k, int flags, int in0, int in1, int inpl, int inpl_to, int out,
@@ -329,6 +333,14 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
         if (pending_get >= 0 && stream == 0) {
             o.flags |= DOPF_GET_BEFORE; o.get_in = pending_get; o.t = pending_get_t;
             pending_get = -1;
+        }
+        if (fuse_build && type == DOP_MMA_NT && !ops.empty() && !(o.flags & DOPF_GET_BEFORE)) {
+            SymOp& p = ops.back();
+            if (p.stream == 0 && p.type == DOP_BUILD && p.I == I && p.J == J && p.flags == 0) {
+                o.flags |= DOPF_BUILD_FIRST; o.t = p.t;
+                p = o;
+                return;
+            }
         }
         ops.push_back(o);
     };
@@ -625,8 +637,9 @@ inline DagProgram build_dag_program_impl(int NT, int nslot, int mode, bool all_s
                     int q = victim(false);                  // not one of this op's operand slots (busy) ...
                     if (q < 0) {                            // ... unless nothing else is free: then after a barrier
                         const unsigned keep = busy;
-                        if (d.slotA >= 0) busy &= ~(1u << d.slotA);
-                        if (d.slotB >= 0) busy &= ~(1u << d.slotB);
+                        // (not the slot this op's own bulk store is reading from)
+                        if (d.slotA >= 0 && d.slotA != d.st_slot) busy &= ~(1u << d.slotA);
+                        if (d.slotB >= 0 && d.slotB != d.st_slot) busy &= ~(1u << d.slotB);
                         q = victim(false);
                         busy = keep;
                         if (q >= 0) d.flags |= DOPF_PUT_BARRIER;
@@ -804,6 +817,7 @@ inline std::string dag_verify(const DagProgram& P) {
             }
             switch (d.type) {
             case DOP_MMA_NT:
+                if (d.flags & DOPF_BUILD_FIRST) acc_owner = tid_of(TK_U, I, J);
                 if (acc_owner != tid_of(TK_U, I, J)) { snprintf(buf, sizeof buf, "bulk op %d updates accumulators that belong to another tile", ib); return buf; }
                 if (!(e = expect(d.slotA, tid_of(TK_L, I, k), "A", 0, ib)).empty()) return e;
                 if (!(e = expect(d.slotB, tid_of(TK_L, J, k), "B", 0, ib)).empty()) return e;

@@ -563,21 +563,11 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         }
         TRW(i, 3);
         PHE(41);
-        PHB(42);
-        for (int s = 0; s < MAX_SLOTS; ++s)
-            if ((wait_mask >> s) & 1) {
-                mbar_wait(&bars[s], (phases >> s) & 1u);
-                phases ^= 1u << s;
-            }
-        PHE(42);
-        PHB(42 + type);
-        TRB(i, 1);
-        TRW(i, 4);
         const double* A = slots + (size_t)(sA < 0 ? 0 : sA) * TILE_ELEMS;
         const double* Bt = slots + (size_t)(sB < 0 ? 0 : sB) * TILE_ELEMS;
         double* C = slots + (size_t)(sC < 0 ? 0 : sC) * TILE_ELEMS;
 
-        if (type == DOP_BUILD || (type == DOP_P2_MMA && (flags & DOPF_LAST))) {
+        if (type == DOP_BUILD || (flags & DOPF_BUILD_FIRST) || (type == DOP_P2_MMA && (flags & DOPF_LAST))) {
             if (!a.resident) {            // slice mode: stage the coordinates (and alpha) of the two tile rows
                 bool staged = false;
                 if (cur_r != I) { stage_slice(sl_r, gd, hfull, I, DAG_BULK_THREADS); cur_r = I; staged = true; }
@@ -596,16 +586,27 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
         const double* uc_p = a.resident ? us_all + TS * J : sl_c + d * TS;
         const int ldz = a.resident ? Np : TS;
 
+        // a covariance tile fused with its first update is generated while the operand tiles are still in flight
+        // (single call site for both kinds of op; a plain BUILD op has no tile to wait for)
+        if (type == DOP_BUILD || (flags & DOPF_BUILD_FIRST))
+            dag_build<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab);
+        PHB(42);
+        for (int s = 0; s < MAX_SLOTS; ++s)
+            if ((wait_mask >> s) & 1) {
+                mbar_wait(&bars[s], (phases >> s) & 1u);
+                phases ^= 1u << s;
+            }
+        PHE(42);
+        PHB(42 + type);
+        TRB(i, 1);
+        TRW(i, 4);
         if (flags & DOPF_GET_BEFORE) dag_acc_load(acc, C, wt);  // partial tile P(I,J) continues in the accumulators
 #ifdef FAB_EXP_TWICE          // experiment: every op body twice (same instructions: second run = warm instruction caches)
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
 #endif
         switch (type) {
-        case DOP_BUILD: {
-            dag_build<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab);
-            break;
-        }
+        case DOP_BUILD: break;            // (generated above)
         case DOP_MMA_NT:
             dag_mma<false, true, true>(acc, A, Bt, wt, KR_ZERO, KR_FULL, I == J);
             break;
