@@ -42,9 +42,10 @@ WALKERS_PER_GPU = 128
 WORKLOAD = ("BASELINE configs[1]: CNN-CIFAR10 space (5 hyper-parameters) + s, N=256, D=6, P=9, 128 walkers per GPU, "
             "Matern52 x (linear+const) basis kernel, FP64")
 # dram__bytes_read.sum + dram__bytes_write.sum of one gp_dag_kernel launch from the committed ncu --set full capture
-TRAFFIC_BYTES_PER_LAUNCH = 168960 + 1181952
-TRAFFIC_SOURCE = ("profiles/r02k_ncu_full_raw.csv: dram__bytes_read.sum 169 KB + dram__bytes_write.sum 1.18 MB per "
-                  "launch of 128 evals (algorithmic bytes 128 x 14.4 KB = 1.84 MB; tiles stream through L2 only)")
+TRAFFIC_BYTES_PER_LAUNCH = 195328 + 2679552
+TRAFFIC_SOURCE = ("profiles/r02p_ncu_full_raw.csv: dram__bytes_read.sum 195 KB + dram__bytes_write.sum 2.68 MB per "
+                  "launch of 128 evals (algorithmic bytes 128 x 14.4 KB = 1.84 MB; the writes are write-through tiles of the "
+                  "41 MB L2-resident workspace that the profiler's cache flush pushes out; no tile is read back from DRAM)")
 # es_entropy_kernel: one launch = 2048 candidates x 128 models; reads the per-model coefficients / innovations and
 # the per-(candidate, model) scalars, writes 2 MB of partial sums (absorbed by L2 during the capture)
 ES_TRAFFIC_BYTES_PER_LAUNCH = 3663616 + 0

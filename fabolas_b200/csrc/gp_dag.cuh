@@ -588,8 +588,12 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
 
         // a covariance tile fused with its first update is generated while the operand tiles are still in flight
         // (single call site for both kinds of op; a plain BUILD op has no tile to wait for)
-        if (type == DOP_BUILD || (flags & DOPF_BUILD_FIRST))
+        TRB(i, 1);
+        if (type == DOP_BUILD || (flags & DOPF_BUILD_FIRST)) {
+            PHB(43);
             dag_build<DD>(acc, zr_p, zc_p, ur_p, uc_p, ldz, h, N, gd.family, I, J, wt, etab);
+            PHE(43);
+        }
         PHB(42);
         for (int s = 0; s < MAX_SLOTS; ++s)
             if ((wait_mask >> s) & 1) {
@@ -597,8 +601,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
                 phases ^= 1u << s;
             }
         PHE(42);
-        PHB(42 + type);
-        TRB(i, 1);
+        if (type != DOP_BUILD) PHB(42 + type);
         TRW(i, 4);
         if (flags & DOPF_GET_BEFORE) dag_acc_load(acc, C, wt);  // partial tile P(I,J) continues in the accumulators
 #ifdef FAB_EXP_TWICE          // experiment: every op body twice (same instructions: second run = warm instruction caches)
@@ -710,7 +713,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
             dag_acc_store(acc, C, wt);
             fence_proxy_async();
         }
-        PHE(42 + type);
+        if (type != DOP_BUILD) PHE(42 + type);
         TRB(i, 2);
         TRW(i, 5);
         __syncwarp();
