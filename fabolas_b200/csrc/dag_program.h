@@ -57,7 +57,10 @@ constexpr int DAG_MAX_LOADS = 6;
 // A reload is issued at most this many ops ahead of its consumer.  Measured (N = 256, ll+grad): 1 -> 267 us, 2 -> 270,
 // 3 -> 272, 4 -> 275, 6 -> 280: one op (~2 us) covers the L2 / HBM latency of a tile, and a reload hoisted further
 // drags the cross-stream waits of its slot to an earlier op.  N = 2048 does not care (slot availability decides).
-constexpr int DAG_PREFETCH_DEPTH = 1;
+#ifndef FAB_DAG_PREFETCH_DEPTH
+#define FAB_DAG_PREFETCH_DEPTH 1
+#endif
+constexpr int DAG_PREFETCH_DEPTH = FAB_DAG_PREFETCH_DEPTH;
 // List scheduling of the bulk stream: tasks that become ready within this many (estimated) microseconds compete with
 // the ready ones (see the scheduling loop).
 constexpr double DAG_LOOKAHEAD_US = 3.0;   // measured at N = 256: 0 -> 256.4 / 132.4 us (ll+grad / ll), 2..4 -> 253.6 / 129.0, 8 -> 255.6 / 131.2
