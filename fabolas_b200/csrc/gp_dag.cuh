@@ -353,9 +353,12 @@ __device__ __forceinline__ void contract_acc(const DagAcc& acc, double* gsum_w,
 // other (the device-resident ensemble sampler, mcmc.cuh): `first` marks the CTA's first one (exp table and
 // mbarriers are set up once), `phases` carries the mbarrier parities of the bulk warps across evaluations, and
 // the caller separates two evaluations by a __syncthreads().
-template <int DD>
+// `side`: scalar work of the caller that does not depend on the result (the sampler's prior density and acceptance
+// draw); thread 0 runs it when the bulk stream has finished its program and would otherwise only wait for the chain.
+struct DagNoSide { __device__ __forceinline__ void operator()() const {} };
+template <int DD, class Side = DagNoSide>
 __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned char* smem_raw, unsigned& phases,
-                                         const bool first) {
+                                         const bool first, Side side = Side()) {
     const GpData& gd = a.gd;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int Np = gd.Np, N = gd.N, Pk = gd.Pk;
@@ -721,6 +724,7 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     }
     PHB(51);
 
+    if (tid == 0) side();
     // the chain has published the log-likelihood, the failure flag and its share of alpha
     if (lane == 0) spin_until(&sync[1], 2 * a.nchain + 1);
     __syncwarp();

@@ -118,17 +118,26 @@ __host__ __device__ inline double lognorm1_logpdf(double x) {
 //   ES (entropy_search.py:49-75): p = [cov, lamb_0..lamb_{d-1}, noise];  0 < cov < 100, same boxes;
 //       theta = [cov, lamb...], yerr2 = noise
 // Returns -inf outside the support (theta is then left untouched and no likelihood is evaluated).
-__host__ __device__ inline double mcmc_log_prior(int prior, const double* p, int P, int d, double* theta, double* yerr2) {
+// Two halves, so that the sampler can evaluate the density (two logs and an exponential integral) next to the
+// likelihood instead of in front of it: the box test + decode, and the density inside the box.
+__host__ __device__ inline bool mcmc_prior_decode(int prior, const double* p, int P, int d, double* theta, double* yerr2) {
     const double cov = p[0], noise = p[P - 1];
     const double cov_hi = prior == MCMC_PRIOR_FABOLAS ? 20.0 : 100.0;
     bool ok = (cov > 0.0) && (cov < cov_hi) && (noise > -20.0) && (noise < 20.0) && !(noise < 0.0);
     for (int k = 1; k < P - 1; ++k) ok = ok && (p[k] > -9.0) && (p[k] < 2.0);
-    if (!ok) return -INFINITY;
+    if (!ok) return false;
     theta[0] = cov;
     for (int k = 0; k < d; ++k) theta[1 + k] = prior == MCMC_PRIOR_FABOLAS ? exp(p[1 + k]) : p[1 + k];
     if (prior == MCMC_PRIOR_FABOLAS) { theta[1 + d] = p[1 + d]; theta[2 + d] = p[2 + d]; }
     *yerr2 = noise;
-    return lognorm1_logpdf(cov) + horseshoe_logpdf(noise, 0.1);
+    return true;
+}
+__host__ __device__ inline double mcmc_prior_density(const double* p, int P) {
+    return lognorm1_logpdf(p[0]) + horseshoe_logpdf(p[P - 1], 0.1);
+}
+__host__ __device__ inline double mcmc_log_prior(int prior, const double* p, int P, int d, double* theta, double* yerr2) {
+    if (!mcmc_prior_decode(prior, p, P, d, theta, yerr2)) return -INFINITY;
+    return mcmc_prior_density(p, P);
 }
 
 // Grid-wide barrier number `gen` (1, 2, ...) of a cooperative launch: every CTA's thread 0 arrives with
@@ -191,24 +200,27 @@ __device__ __forceinline__ void box_barrier(const McmcArgs& m, unsigned& gen, un
 
 // Evaluate the log-probability of the P-vector in m.q (this CTA's record): thread 0 decodes the prior, the whole
 // CTA runs the likelihood.  Result valid in thread 0.
-template <int DD>
+// `extra`: more scalar work of thread 0 that can run next to the likelihood (the acceptance draw of the move).
+template <int DD, class Extra>
 __device__ __forceinline__ double mcmc_log_prob(const McmcArgs& m, unsigned char* smem_raw, unsigned& phases, bool& first,
-                                                int* flag) {
+                                                int* flag, Extra extra) {
     const int cta = blockIdx.x;
     double prior_lp = 0.0;
     PHB(33);
     if (threadIdx.x == 0) {
-        prior_lp = mcmc_log_prior(m.prior, m.q + (size_t)cta * m.P, m.P, m.dag.gd.d,
+        // box test and decode only: the density is evaluated by this thread inside dag_eval, while the bulk stream waits
+        // for the chain's last diagonal tile (NaN cannot occur: every term is finite inside the box, +inf at noise == 0)
+        *flag = mcmc_prior_decode(m.prior, m.q + (size_t)cta * m.P, m.P, m.dag.gd.d,
                                   const_cast<double*>(m.dag.theta) + (size_t)cta * m.dag.gd.Pk,
-                                  const_cast<double*>(m.dag.yerr2) + cta);
-        *flag = prior_lp > -INFINITY ? 1 : 0;     // NaN cannot occur: every term is finite inside the box (+inf at noise == 0)
+                                  const_cast<double*>(m.dag.yerr2) + cta) ? 1 : 0;
     }
     __syncthreads();
     PHE(33);
     const bool run = *flag != 0;                  // uniform over the CTA
     PHB(34);
     if (run) {
-        dag_eval<DD>(m.dag, cta, smem_raw, phases, first);
+        auto side = [&]() { prior_lp = mcmc_prior_density(m.q + (size_t)cta * m.P, m.P); extra(); };
+        dag_eval<DD>(m.dag, cta, smem_raw, phases, first, side);
         first = false;
     }
     __syncthreads();
@@ -283,7 +295,12 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
             }
             __syncthreads();
             PHE(32);
-            const double new_lp = mcmc_log_prob<DD>(m, smem_raw, phases, first, flag);
+            // (thread 0) the acceptance draw does not depend on the likelihood either
+            double logu = 0.0;
+            auto draw = [&]() {
+                if (!init) { const Philox4 r = mcmc_rand(m.seed, iter, 3 + split, mm); logu = log(uniform53(r.x, r.y)); }
+            };
+            const double new_lp = mcmc_log_prob<DD>(m, smem_raw, phases, first, flag, draw);
             PHB(35);
             if (tid == 0 && init) {
                 if (m.world > 1) { for (int r = 0; r < W; ++r) m.peer_lp[r][s] = new_lp; }
@@ -291,8 +308,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) mcmc_stretch_kernel(McmcArgs m
             } else if (tid == 0) {
                 const double old_lp = ld_cg(&m.lp[s]);
                 const double lnpdiff = zfac + new_lp - old_lp;          // NaN (-inf - -inf) compares false: rejected
-                const Philox4 r = mcmc_rand(m.seed, iter, 3 + split, mm);
-                const bool acc = lnpdiff > log(uniform53(r.x, r.y));
+                if (!(new_lp > -INFINITY)) draw();                       // (no likelihood was evaluated: draw now)
+                const bool acc = lnpdiff > logu;
                 if (acc) {
                     if (m.world > 1) {                                  // every replica, this rank's included
                         for (int r = 0; r < W; ++r) {
