@@ -39,6 +39,8 @@ SIGNATURES = {
     "fab_ctx_get_timing": (_c_int, [_vp, ctypes.POINTER(_c_dbl), _c_int]),
     "fab_gp_set_data": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_dbl, _c_dbl]),
     "fab_gp_loglik_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
+    "fab_gp_loglik_batch_host": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
+    "fab_ctx_synchronize": (_c_int, [_vp]),
     "fab_gp_factorize_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
     "fab_gp_fit_batch": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp]),
     "fab_gp_predict_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp]),
@@ -216,6 +218,33 @@ class Engine:
         self._check(self.lib.fab_gp_loglik_batch(self._ctx, _ptr(theta), _ptr(yerr2), B, _ptr(ll), _ptr(g),
                                                  _ptr(info)), "fab_gp_loglik_batch")
         return (ll, g, info) if grad else (ll, info)
+
+    def loglik_host(self, theta, yerr2, grad: bool = False, out=None):
+        """loglik() for HOST tensors (float64, contiguous; info int32): pinned tensors are read and written by the kernel
+        itself over the bus, pageable ones are staged by the library.  Enqueued on the engine's stream: synchronise
+        (Engine.synchronize or torch.cuda.synchronize) before reading the outputs.  Returns (ll, [grad,] info)."""
+        if theta.device.type != "cpu" or yerr2.device.type != "cpu":
+            raise ValueError("loglik_host takes host tensors; use loglik for device tensors")
+        if theta.dtype != torch.float64 or yerr2.dtype != torch.float64 or not theta.is_contiguous() or not yerr2.is_contiguous():
+            raise ValueError("float64 contiguous host tensors expected")
+        if theta.dim() != 2 or theta.shape[1] != self.Pk or yerr2.numel() != theta.shape[0]:
+            raise ValueError(f"theta must be B x {self.Pk}, yerr2 B")
+        B = theta.shape[0]
+        if out is not None:
+            ll, g, info = out
+        else:
+            pin = theta.is_pinned()
+            ll = torch.empty(B, dtype=torch.float64, pin_memory=pin)
+            info = torch.empty(B, dtype=torch.int32, pin_memory=pin)
+            g = torch.empty(B, self.Pk + 1, dtype=torch.float64, pin_memory=pin) if grad else None
+        if ll.numel() != B or info.numel() != B or info.dtype != torch.int32 or (grad and (g is None or g.numel() != B * (self.Pk + 1))):
+            raise ValueError("out tensors do not match the batch")
+        self._check(self.lib.fab_gp_loglik_batch_host(self._ctx, _ptr(theta), _ptr(yerr2), B, _ptr(ll), _ptr(g) if grad else None,
+                                                      _ptr(info)), "fab_gp_loglik_batch_host")
+        return (ll, g, info) if grad else (ll, info)
+
+    def synchronize(self):
+        self._check(self.lib.fab_ctx_synchronize(self._ctx), "fab_ctx_synchronize")
 
     def factorize(self, theta, yerr2):
         theta, yerr2 = self._theta(theta, yerr2)

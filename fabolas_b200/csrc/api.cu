@@ -32,6 +32,9 @@ struct fab_ctx {
     size_t capL = 0, capZ = 0, capA = 0, capW = 0;
     double* dTheta = nullptr; size_t capT = 0;   // hyper-parameters of the resident models
     double* dYerr2 = nullptr; size_t capY = 0;
+    double* hTheta = nullptr; size_t capHT = 0;  // staging of fab_gp_loglik_batch_host for pageable host memory
+    double* hYerr2 = nullptr; size_t capHY = 0;
+    double* hOut = nullptr; size_t capHO = 0;
     int* dInfo = nullptr; size_t capI = 0;
     bool resident = false;  // factorize_batch completed: W, alpha, theta resident
     // Entropy-Search state (fab_es_setup) and scratch for information-gain sweeps
@@ -189,6 +192,7 @@ int fab_ctx_destroy(fab_ctx* c) {
     if (!c) return FAB_EINVAL;
     cudaSetDevice(c->device);
     cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dTheta); cudaFree(c->dYerr2); cudaFree(c->dInfo);
+    cudaFree(c->hTheta); cudaFree(c->hYerr2); cudaFree(c->hOut);
     cudaFree(c->es.rl); cudaFree(c->es.vrl); cudaFree(c->es.coef); cudaFree(c->es.logP); cudaFree(c->es.logU);
     cudaFree(c->es.base); cudaFree(c->es.omega);
     cudaFree(c->sc_mu); cudaFree(c->sc_var); cudaFree(c->sc_dot); cudaFree(c->sc_c0); cudaFree(c->sc_part);
@@ -331,7 +335,7 @@ static int dag_setup(fab_ctx* c, int B, int mode, size_t smem_limit, DagArgs* ou
     a.gd = gd; a.wk = c->wk; a.theta = nullptr; a.yerr2 = nullptr; a.ll = nullptr; a.info = nullptr; a.grad = nullptr;
     a.bulk = dv.bulk; a.chain = dv.chain; a.nbulk = dv.nbulk; a.nchain = dv.nchain;
     a.nslot = nslot; a.mode = mode; a.resident = resident; a.ntiles = ntiles; a.wk_spill = c->wkSpill;
-    a.peer.world = 0;
+    a.peer.world = 0; a.host_io = 0;
     *out = a;
     *smem_out = dag_smem_bytes(nslot, gd.d, resident ? gd.Np : 0);
     c->resident = false;
@@ -344,12 +348,12 @@ static int dag_setup(fab_ctx* c, int B, int mode, size_t smem_limit, DagArgs* ou
 
 // One launch of the fused kernel (one CTA per walker).
 static int launch_dag(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info, double* grad,
-                      int mode, bool exchange = false) {
+                      int mode, bool exchange = false, bool host_io = false) {
     DagArgs a;
     size_t smem = 0;
     const int rc = dag_setup(c, B, mode, (size_t)c->smem_optin, &a, &smem);
     if (rc != FAB_OK) return rc;
-    a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info; a.grad = grad;
+    a.theta = theta; a.yerr2 = yerr2; a.ll = ll; a.info = info; a.grad = grad; a.host_io = host_io ? 1 : 0;
     if (exchange) {
         const fab_ctx::Peer& p = c->peer;
         const size_t parity = (size_t)(p.steps & 1ull) * p.buf_bytes;
@@ -377,6 +381,52 @@ int fab_gp_loglik_batch(fab_ctx* c, const double* theta, const double* yerr2, in
     if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
     FAB_CUDA(c, cudaSetDevice(c->device));
     return launch_dag(c, theta, yerr2, B, ll, info, grad, grad ? DAG_GRAD : DAG_LL);
+}
+
+// Device alias of a host pointer the CUDA driver knows (cudaHostAlloc / cudaHostRegister / torch pin_memory): the fused
+// kernel reads and writes such memory directly.  nullptr for pageable memory.
+static void* mapped_alias(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
+int fab_gp_loglik_batch_host(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, double* grad,
+                             int* info) {
+    if (!c) return FAB_EINVAL;
+    if (!c->has_data) return fail(c, FAB_ESTATE, "fab_gp_set_data has not been called");
+    if (!theta || !yerr2 || !ll || !info || B < 1) return fail(c, FAB_EINVAL, "bad argument");
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    const int Pk = c->gd.Pk;
+    const double* d_theta = static_cast<const double*>(mapped_alias(theta));
+    const double* d_yerr2 = static_cast<const double*>(mapped_alias(yerr2));
+    double* d_ll = static_cast<double*>(mapped_alias(ll));
+    int* d_info = static_cast<int*>(mapped_alias(info));
+    double* d_grad = grad ? static_cast<double*>(mapped_alias(grad)) : nullptr;
+    if (d_theta && d_yerr2 && d_ll && d_info && (!grad || d_grad))       // zero-copy: the kernel does the transfers itself
+        return launch_dag(c, d_theta, d_yerr2, B, d_ll, d_info, d_grad, grad ? DAG_GRAD : DAG_LL, false, true);
+    // pageable host memory: staged through buffers of the context (the copies are stream-ordered)
+    int rc;
+    if ((rc = ensure(c, &c->hTheta, &c->capHT, (size_t)B * Pk)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->hYerr2, &c->capHY, (size_t)B)) != FAB_OK) return rc;
+    if ((rc = ensure(c, &c->hOut, &c->capHO, (size_t)B * (Pk + 3))) != FAB_OK) return rc;
+    double* o_ll = c->hOut; double* o_grad = c->hOut + B; int* o_info = reinterpret_cast<int*>(c->hOut + (size_t)B * (Pk + 2));
+    FAB_CUDA(c, cudaMemcpyAsync(c->hTheta, theta, sizeof(double) * B * Pk, cudaMemcpyHostToDevice, c->stream));
+    FAB_CUDA(c, cudaMemcpyAsync(c->hYerr2, yerr2, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+    rc = launch_dag(c, c->hTheta, c->hYerr2, B, o_ll, o_info, grad ? o_grad : nullptr, grad ? DAG_GRAD : DAG_LL);
+    if (rc != FAB_OK) return rc;
+    FAB_CUDA(c, cudaMemcpyAsync(ll, o_ll, sizeof(double) * B, cudaMemcpyDeviceToHost, c->stream));
+    if (grad) FAB_CUDA(c, cudaMemcpyAsync(grad, o_grad, sizeof(double) * B * (Pk + 1), cudaMemcpyDeviceToHost, c->stream));
+    FAB_CUDA(c, cudaMemcpyAsync(info, o_info, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
+    return FAB_OK;
+}
+
+int fab_ctx_synchronize(fab_ctx* c) {
+    if (!c) return FAB_EINVAL;
+    FAB_CUDA(c, cudaSetDevice(c->device));
+    FAB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FAB_OK;
 }
 
 int fab_gp_factorize_batch(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, int* info) {

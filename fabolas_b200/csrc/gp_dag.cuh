@@ -135,6 +135,8 @@ struct DagArgs {
     const DagOp* chain;
     int nbulk, nchain;
     int nslot, mode;
+    int host_io;           // 1: theta / yerr2 (and ll / info / grad) are mapped HOST memory: one warp fetches the walker's
+                           //    record over PCIe and the CTA decodes it from shared memory (fab_gp_loglik_batch_host)
     int resident;          // 1: scaled coordinates, z, accw, alpha of all Np rows live in shared memory
     int ntiles;            // NT (NT + 1) / 2: workspace tile indices >= ntiles address the spill region wk_spill
     double* wk_spill;      // B x NT tiles (FACTOR mode only: inverted diagonal tiles that had to leave shared memory)
@@ -400,7 +402,17 @@ __device__ __forceinline__ void dag_eval(const DagArgs& a, const int b, unsigned
     };
     ring_fetch(0); ring_fetch(1); ring_fetch(2);
 
-    const Hyper hfull = decode_hyper(gd, a.theta + (size_t)b * Pk, a.yerr2[b]);
+    const double* thp = a.theta + (size_t)b * Pk;
+    double ye;
+    if (a.host_io) {                      // zero-copy input: Pk + 1 loads per CTA cross the bus, not Pk + 1 per warp
+        if (tid <= Pk) part[tid] = (tid < Pk) ? thp[tid] : a.yerr2[b];
+        __syncthreads();
+        thp = part;                       // (free until the first panel-solve epilogue)
+        ye = part[Pk];
+    } else {
+        ye = a.yerr2[b];
+    }
+    const Hyper hfull = decode_hyper(gd, thp, ye);
     Hyper h;                              // scalars only: hfull.scale[] is indexed dynamically and lives in local memory
     h.amp = hfull.amp; h.inv_g2 = hfull.inv_g2; h.cb = hfull.cb; h.diag_add = hfull.diag_add;
     double* Lw = a.wk.Lw ? a.wk.Lw + (size_t)b * a.ntiles * TILE_ELEMS : nullptr;

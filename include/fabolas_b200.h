@@ -73,6 +73,17 @@ int fab_gp_set_data(fab_ctx* ctx, int family, const double* X, int N, int D, con
 int fab_gp_loglik_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll,
                         double* grad, int* info);
 
+/* The same call with HOST buffers -- the reference's own calling pattern: fabolas.log_likelihood is handed numpy
+ * arrays by emcee and returns floats (fabolas.py:16-66, 103-117).  Buffers the CUDA driver knows (cudaHostAlloc,
+ * cudaHostRegister, torch pin_memory) are read and written by the kernel itself over the bus (zero-copy: one warp per
+ * walker fetches the Pk + 1 inputs, the results are posted stores -- no separate copy engine transfers around a
+ * 0.24 ms kernel); pageable memory is staged through buffers of the context.  Stream-ordered: the outputs are valid
+ * once the context's stream has been synchronised (fab_ctx_synchronize, or the caller's own stream sync).            */
+int fab_gp_loglik_batch_host(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll,
+                             double* grad, int* info);
+/* Blocks until everything enqueued on the context's stream has completed. */
+int fab_ctx_synchronize(fab_ctx* ctx);
+
 /* Cholesky factors of B models into the context workspace (tiled, swizzled; test / debug use).  */
 int fab_gp_factorize_batch(fab_ctx* ctx, const double* theta, const double* yerr2, int B, double* ll,
                            int* info);

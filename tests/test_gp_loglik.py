@@ -216,3 +216,34 @@ def test_not_positive_definite_is_data_gpu(gpu_engine):
     ok = [0, 2, 3]
     ref = go.loglik_batch(0, X, y, y.mean(), theta[ok], yerr2[ok], amp_axes=3)
     assert np.all(info[ok] == 0) and np.max(np.abs(ll[ok] - ref) / np.abs(ref)) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [True, False])
+def test_loglik_host_buffers_gpu(pinned):
+    """fab_gp_loglik_batch_host (host buffers, the reference's calling pattern fabolas.py:103-117): zero-copy for pinned
+    memory, staged for pageable memory -- bit-identical to the device-buffer entry either way, ll and ll+grad."""
+    import torch
+    from fabolas_b200 import Engine
+    from fabolas_b200.workloads import gp_workload
+    w = gp_workload(2, n_walkers=37)
+    eng = Engine()
+    eng.set_data(w["family"], w["X"], w["y"], w["mean"], w["amp_mult"])
+    th = torch.from_numpy(w["theta"].copy())
+    ye = torch.from_numpy(w["yerr2"].copy())
+    ye[3] = -5.0                                   # a walker whose covariance is not positive definite
+    if pinned:
+        th, ye = th.pin_memory(), ye.pin_memory()
+    ll_d, g_d, info_d = eng.loglik(th.cuda(), ye.cuda(), grad=True)
+    ll_h, g_h, info_h = eng.loglik_host(th, ye, grad=True)
+    eng.synchronize()
+    assert ll_h.is_pinned() == pinned
+    assert torch.equal(ll_h, ll_d.cpu()) and torch.equal(info_h, info_d.cpu())
+    assert torch.equal(torch.nan_to_num(g_h, nan=123.0), torch.nan_to_num(g_d.cpu(), nan=123.0))
+    assert info_h[3] > 0 and ll_h[3] == -float("inf")
+    ll2, info2 = eng.loglik_host(th, ye)
+    eng.synchronize()
+    ll2_d, _ = eng.loglik(th.cuda(), ye.cuda())
+    assert torch.equal(ll2, ll2_d.cpu()) and torch.equal(info2, info_d.cpu())
+    with pytest.raises(ValueError):
+        eng.loglik_host(th.cuda(), ye.cuda())
