@@ -386,10 +386,14 @@ int fab_gp_loglik_batch(fab_ctx* c, const double* theta, const double* yerr2, in
 // Device alias of a host pointer the CUDA driver knows (cudaHostAlloc / cudaHostRegister / torch pin_memory): the fused
 // kernel reads and writes such memory directly.  nullptr for pageable memory.
 static void* mapped_alias(const void* p) {
+#ifdef FAB_CUSIM
+    return const_cast<void*>(p);                       // (the emulator's "device" memory is host memory)
+#else
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
     return at.devicePointer;
+#endif
 }
 
 int fab_gp_loglik_batch_host(fab_ctx* c, const double* theta, const double* yerr2, int B, double* ll, double* grad,

@@ -83,6 +83,20 @@ def test_not_positive_definite_is_data_emulated(sim_engine):
     assert ref[1] == -np.inf and abs(ll[0] - ref[0]) < TOL * abs(ref[0])
 
 
+def test_host_buffer_entry_emulated(sim_engine):
+    """fab_gp_loglik_batch_host on the emulator: the kernel's host-input mode (one warp stages the walker's record in
+    shared memory) gives exactly what the device-buffer entry gives."""
+    import torch
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, (70, 3)); y = rng.standard_normal(70)
+    theta = np.column_stack([rng.uniform(-1, 1, 3), rng.uniform(0, 2, (3, 3))]); yerr2 = rng.uniform(1e-3, 0.1, 3)
+    sim_engine.set_data(0, X, y, float(y.mean()), 3)
+    ll, g, info = sim_engine.loglik(theta, yerr2, grad=True)
+    ll_h, g_h, info_h = sim_engine.loglik_host(torch.from_numpy(theta), torch.from_numpy(yerr2), grad=True)
+    sim_engine.synchronize()
+    assert torch.equal(ll_h, ll) and torch.equal(g_h, g) and torch.equal(info_h, info)
+
+
 def test_argument_errors_emulated(sim_engine):
     from fabolas_b200 import FabolasError
     X, y, theta, yerr2 = _problem(10, 2, 0, 2)
