@@ -345,10 +345,10 @@ def leg_loglik(cx, args, peak_dmma, dgemm_tf):
 
     # one GPU: the host-buffer entry point (fab_gp_loglik_batch_host) -- the kernel itself reads the pinned inputs and
     # writes the pinned results over the bus: the same bytes cross, without two copy-engine transfers around a 0.24 ms kernel
-    thh_view, yeh_view = in_host[:Bg * Pk].view(Bg, Pk), in_host[Bg * Pk:]
-    gh_view, llh_view = out_host[:Bg * P].view(Bg, P), out_host[Bg * P:Bg * P + Bg]
     info_host = torch.empty(Bg, dtype=torch.int32).pin_memory()
     if world == 1:
+        thh_view, yeh_view = in_host[:Bg * Pk].view(Bg, Pk), in_host[Bg * Pk:]
+        gh_view, llh_view = out_host[:Bg * P].view(Bg, P), out_host[Bg * P:Bg * P + Bg]
         eng.loglik_host(thh_view, yeh_view, grad=True, out=(llh_view, gh_view, info_host))
         torch.cuda.synchronize()
         ll_c, g_c, info_c = eng.loglik(theta_d, yerr2_d, grad=True)
