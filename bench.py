@@ -346,6 +346,7 @@ def leg_loglik(cx, args, peak_dmma, dgemm_tf):
     # one GPU: the host-buffer entry point (fab_gp_loglik_batch_host) -- the kernel itself reads the pinned inputs and
     # writes the pinned results over the bus: the same bytes cross, without two copy-engine transfers around a 0.24 ms kernel
     info_host = torch.empty(Bg, dtype=torch.int32).pin_memory()
+    thp_view, yep_view = in_host[:Bg * Pk].view(Bg, Pk), in_host[Bg * Pk:]
     if world == 1:
         thh_view, yeh_view = in_host[:Bg * Pk].view(Bg, Pk), in_host[Bg * Pk:]
         gh_view, llh_view = out_host[:Bg * P].view(Bg, P), out_host[Bg * P:Bg * P + Bg]
@@ -359,11 +360,11 @@ def leg_loglik(cx, args, peak_dmma, dgemm_tf):
         if world == 1:
             eng.loglik_host(thh_view, yeh_view, grad=True, out=(llh_view, gh_view, info_host))
             return
-        in_dev.copy_(in_host, non_blocking=True)
-        if exchange == "peer":
-            eng.loglik_exchange(th_view, ye_view, grad=True, out=(ll_loc, g_loc, info_loc))
+        if exchange == "peer":                 # (pinned host inputs: fetched by the kernel itself, no H2D copy)
+            eng.loglik_exchange(thp_view, yep_view, grad=True, out=(ll_loc, g_loc, info_loc))
             out_host.copy_(eng.peer_wait(), non_blocking=True)
         else:
+            in_dev.copy_(in_host, non_blocking=True)
             eng.loglik(th_view, ye_view, grad=True, out=(ll_loc, g_loc, info_loc))
             if world > 1:
                 dist.all_gather_into_tensor(packed_all, packed)
@@ -431,7 +432,8 @@ def leg_loglik(cx, args, peak_dmma, dgemm_tf):
                 "h2d_bytes_per_step": int(in_host.numel() * 8), "d2h_bytes_per_step": int(out_host.numel() * 8) + (int(info_host.numel() * 4) if world == 1 else 0),
                 "what": ("pinned host [theta | yerr2] -> Engine.loglik_host (fab_gp_loglik_batch_host: the kernel reads the inputs "
                          "and writes [grad | ll | info] over the bus itself, zero-copy) -> pinned host results" if world == 1 else
-                         "pinned host [theta | yerr2] -> H2D -> Engine.loglik" + ("_exchange (fused exchange)" if exchange == "peer" else "")
+                         ("pinned host [theta | yerr2] -> Engine.loglik_exchange (fused exchange; the kernel fetches the pinned inputs itself)"
+                          if exchange == "peer" else "pinned host [theta | yerr2] -> H2D -> Engine.loglik -> all-gather")
                          + " -> D2H of the gathered rows of all ranks")},
         "exchange": {"none": "none (one GPU)", "peer": "fused into the kernel: every CTA stores its walker's row into every rank's "
                      "gather buffer over NVLink peer memory; the last CTA publishes the rank's step number to every rank and waits "

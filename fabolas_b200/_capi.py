@@ -399,8 +399,15 @@ class Engine:
         self.peer_world, self.peer_rank, self.peer_rows = world, rank, int(rows_per_rank)
 
     def loglik_exchange(self, theta, yerr2, grad: bool = False, out=None):
-        """loglik() on this rank's walkers whose result rows also land in every rank's gather buffer."""
-        theta, yerr2 = self._theta(theta, yerr2)
+        """loglik() on this rank's walkers whose result rows also land in every rank's gather buffer.  theta / yerr2 may be
+        PINNED host tensors (B x Pk, B; float64, contiguous): the kernel then fetches them over the bus itself."""
+        if isinstance(theta, torch.Tensor) and theta.device.type == "cpu" and theta.is_pinned() and self.device.type == "cuda":
+            if not (isinstance(yerr2, torch.Tensor) and yerr2.is_pinned() and theta.dtype == yerr2.dtype == torch.float64
+                    and theta.is_contiguous() and yerr2.is_contiguous() and theta.dim() == 2 and theta.shape[1] == self.Pk
+                    and yerr2.numel() == theta.shape[0]):
+                raise ValueError("pinned host inputs: float64 contiguous theta (B x Pk) and yerr2 (B), both pinned")
+        else:
+            theta, yerr2 = self._theta(theta, yerr2)
         B = theta.shape[0]
         if out is not None:
             ll, g, info = out if grad else (out[0], None, out[-1])

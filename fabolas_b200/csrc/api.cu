@@ -746,7 +746,23 @@ int fab_gp_loglik_exchange(fab_ctx* c, const double* theta, const double* yerr2,
     if (B != c->peer.rows_per_rank) return fail(c, FAB_EINVAL, "B must equal the rows_per_rank given to fab_peer_alloc");
     if (c->peer.row_doubles != c->gd.Pk + 3) return fail(c, FAB_ESTATE, "the data changed shape since fab_peer_alloc");
     FAB_CUDA(c, cudaSetDevice(c->device));
-    const int rc = launch_dag(c, theta, yerr2, B, ll, info, grad, grad ? DAG_GRAD : DAG_LL, true);
+    // theta / yerr2 may be pinned HOST memory (both or neither): the kernel then fetches them over the bus itself
+    bool host_in = false;
+#ifndef FAB_CUSIM
+    {
+        cudaPointerAttributes at;
+        const bool th_host = cudaPointerGetAttributes(&at, theta) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        const bool ye_host = cudaPointerGetAttributes(&at, yerr2) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (th_host != ye_host) return fail(c, FAB_EINVAL, "theta and yerr2 must both be device or both be pinned host memory");
+        if (th_host) {
+            theta = static_cast<const double*>(mapped_alias(theta)); yerr2 = static_cast<const double*>(mapped_alias(yerr2));
+            if (!theta || !yerr2) return fail(c, FAB_EINVAL, "host inputs must be pinned (CUDA-registered) memory");
+            host_in = true;
+        }
+    }
+#endif
+    const int rc = launch_dag(c, theta, yerr2, B, ll, info, grad, grad ? DAG_GRAD : DAG_LL, true, host_in);
     if (rc != FAB_OK) return rc;
     c->peer.steps += 1;
     return FAB_OK;

@@ -169,7 +169,8 @@ int fab_kernel_matrix(fab_ctx* ctx, int family, int nu_code, double nu, const do
  *                     handles with any transport
  *   fab_peer_connect  handles: world x 64 bytes (host, rank order); maps the peers' buffers
  *   fab_gp_loglik_exchange  = fab_gp_loglik_batch on this rank's B = rows_per_rank walkers, plus the peer stores and
- *                     the wait for every rank's rows of this step
+ *                     the wait for every rank's rows of this step; theta / yerr2 may be pinned HOST memory (both or
+ *                     neither): the kernel then fetches them over the bus itself, as fab_gp_loglik_batch_host does
  *   fab_peer_wait     enqueues nothing (kept for the call order of the first version of this interface): returns the
  *                     device pointer of this rank's gathered rows of the most recent exchanged step: rows x
  *                     row_doubles, row of walker b of rank r at (r * B + b): [grad (Pk+1; zero when grad was not
