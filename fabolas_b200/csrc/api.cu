@@ -54,6 +54,7 @@ struct fab_ctx {
     int smem_optin = 232448;
     int max_slots = MAX_SLOTS;   // test knob: fewer shared-memory tile slots => exercises the streaming path
     int force_slices = 0;        // test knob: never keep all coordinates resident in the gradient kernel
+    int mcmc_no_cluster = getenv("FAB_MCMC_NO_CLUSTER") != nullptr;   // development: A/B of the cluster launch of small ensembles
     // peer exchange of the likelihood step (gp_dag.cuh PeerTable): one IPC-exported allocation per rank holding two
     // gather buffers (step parity) + arrival counter + error flag; the peers' mappings
     struct Peer {
@@ -841,7 +842,7 @@ static int mcmc_launch(fab_ctx* c, int prior, double* coords, double* log_prob, 
     m.K = K; m.P = P; m.prior = prior; m.nsteps = nsteps; m.init_lp = init_lp != 0;
     m.seed = seed; m.iter0 = iter0; m.a = a_scale;
     m.chain = chain; m.chain_lp = chain_lp; m.nacc = naccepted; m.gbar = c->mcBar;
-    m.world = 1; m.rank = 0; m.xgen0 = 0; m.peer_err = nullptr;
+    m.world = 1; m.rank = 0; m.xgen0 = 0; m.peer_err = nullptr; m.cluster = 0;
     for (int r = 0; r < FAB_MAX_PEERS; ++r) { m.peer_coords[r] = nullptr; m.peer_lp[r] = nullptr; m.peer_flag[r] = nullptr; }
     if (sharded) {
         fab_ctx::McPeer& p = c->mpeer;
@@ -862,7 +863,27 @@ static int mcmc_launch(fab_ctx* c, int prior, double* coords, double* log_prob, 
     void* params[] = {&m};
     void* kern = nullptr;
     FAB_DISPATCH_D(gd.d, kern = reinterpret_cast<void*>(mcmc_stretch_kernel<DD>));
-    FAB_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DAG_THREADS), params, smem, c->stream));
+    // A small ensemble on one GPU (the reference's: 20 walkers, 10 CTAs) runs as ONE thread-block cluster, whose hardware
+    // barrier is the per-half-step barrier; larger grids and sharded chains use the cooperative launch and the counter.
+    bool launched = false;
+    if (!sharded && grid >= 2 && grid <= 16 && !c->mcmc_no_cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DAG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)grid; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters >= 1) {
+            m.cluster = 1;
+            if (cudaLaunchKernelExC(&cfg, kern, params) == cudaSuccess) launched = true;
+            else m.cluster = 0;
+        }
+        cudaGetLastError();                      // (a refused cluster configuration is not an error: fall back)
+    }
+    if (!launched)
+        FAB_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DAG_THREADS), params, smem, c->stream));
 #endif
     FAB_CUDA(c, cudaGetLastError());
     if (c->timing) { FAB_CUDA(c, cudaEventRecord(c->ev[1], c->stream)); c->ev_used = 1; }

@@ -53,6 +53,7 @@ struct McmcArgs {
     int* peer_err;               // local: set when a peer did not show up within ~2 s
     unsigned xgen0;              // cross-GPU barrier generations used by earlier launches
     int world, rank;
+    int cluster;                 // 1: the whole grid is ONE thread-block cluster (<= 16 CTAs): hardware cluster barrier
 };
 
 struct Philox4 { unsigned x, y, z, w; };
@@ -142,7 +143,16 @@ __host__ __device__ inline double mcmc_log_prior(int prior, const double* p, int
 
 // Grid-wide barrier number `gen` (1, 2, ...) of a cooperative launch: every CTA's thread 0 arrives with
 // release semantics and spins with acquire loads; the other threads wait at the block barrier.
-__device__ __forceinline__ void grid_barrier(unsigned* gbar, unsigned gen) {
+__device__ __forceinline__ void grid_barrier(unsigned* gbar, unsigned gen, int cluster = 0) {
+#ifndef FAB_CUSIM
+    if (cluster) {
+        // the grid is one cluster (the reference's own ensemble, 20 walkers = 10 CTAs): the hardware barrier of the
+        // cluster with release / acquire semantics replaces the counter in global memory and its polling round trips
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        return;
+    }
+#endif
     __syncthreads();
 #ifndef FAB_CUSIM
     if (threadIdx.x == 0) {
@@ -173,7 +183,7 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 // visible to every thread of every rank after it (block barrier -> gpu-scope release/acquire -> system-scope
 // fence and flag -> acquire on the peer -> its grid barrier).
 __device__ __forceinline__ void box_barrier(const McmcArgs& m, unsigned& gen, unsigned& xgen) {
-    grid_barrier(m.gbar, ++gen);
+    grid_barrier(m.gbar, ++gen, m.cluster);
     if (m.world > 1) {
         ++xgen;
 #ifndef FAB_CUSIM
